@@ -1,0 +1,125 @@
+"""ctypes binding of libaninerf_b200.so (the C ABI declared in include/aninerf_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libaninerf_b200.so')
+
+N_BONES = 24
+BW_CH = 25
+CHUNK_RAYS = 2048
+FIELD_BW, FIELD_NOVEL_BW, FIELD_NERF = 0, 1, 2
+
+c_float_p = C.POINTER(C.c_float)
+c_i32_p = C.POINTER(C.c_int32)
+c_u8_p = C.POINTER(C.c_uint8)
+
+
+class Camera(C.Structure):
+    _fields_ = [('Kinv', C.c_double * 9), ('R', C.c_double * 9), ('T', C.c_double * 3), ('H', C.c_int32), ('W', C.c_int32)]
+
+
+class Layer(C.Structure):
+    _fields_ = [('W', c_float_p), ('bias_table', c_float_p), ('n_out', C.c_int32), ('k_in', C.c_int32),
+                ('n_tables', C.c_int32), ('relu', C.c_int32)]
+
+
+class Frame(C.Structure):
+    _fields_ = [('A', C.c_void_p), ('R', C.c_void_p), ('Th', C.c_void_p), ('pbw', C.c_void_p), ('tbw', C.c_void_p),
+                ('pbounds', C.c_void_p), ('tbounds', C.c_void_p), ('pbw_dims', C.c_int32 * 3), ('tbw_dims', C.c_int32 * 3),
+                ('latent_index', C.c_int32), ('bw_latent_index', C.c_int32)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [('n_samples', C.c_int32), ('chunk_rays', C.c_int32), ('norm_th', C.c_float), ('white_bkgd', C.c_int32),
+                ('novel_pose', C.c_int32), ('want_bw', C.c_int32), ('bw_precision', C.c_int32), ('nerf_precision', C.c_int32)]
+
+
+class RenderOutputs(C.Structure):
+    _fields_ = [('rgb_map', C.c_void_p), ('acc_map', C.c_void_p), ('depth_map', C.c_void_p), ('raw', C.c_void_p),
+                ('pbw_all', C.c_void_p), ('tbw_all', C.c_void_p), ('sigma_masked', C.c_void_p), ('active_index', C.c_void_p),
+                ('n_active', C.c_void_p), ('chunk_offsets', C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/aninerf_b200.h declares
+_VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+PROTOTYPES = {
+    'aninerf_version': (_I32, []),
+    'aninerf_last_error': (C.c_char_p, []),
+    'aninerf_launch_count': (_I64, []),
+    'aninerf_gen_rays': (_I32, [C.POINTER(Camera), _VP, _VP, _VP]),
+    'aninerf_near_far': (_I32, [c_float_p, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    'aninerf_compact_workspace_bytes': (_I64, [_I64]),
+    'aninerf_compact_rays': (_I32, [_VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
+    'aninerf_sample_points': (_I32, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _I32, _VP, _VP, _VP, _VP]),
+    'aninerf_world_to_pose': (_I32, [_VP, _I64, _VP, _VP, _VP, _VP]),
+    'aninerf_sample_blend_weights': (_I32, [_VP, _I64, _VP, C.POINTER(_I32), _VP, _VP, _VP]),
+    'aninerf_inverse_lbs': (_I32, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_forward_lbs': (_I32, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_composite': (_I32, [_VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'aninerf_net_create': (_I32, [C.POINTER(_VP)]),
+    'aninerf_net_destroy': (_I32, [_VP]),
+    'aninerf_net_load_field': (_I32, [_VP, _I32, C.POINTER(Layer), _I32, c_float_p, c_float_p, c_float_p, c_float_p, _VP]),
+    'aninerf_bw_forward': (_I32, [_VP, _I32, _I32, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _VP]),
+    'aninerf_nerf_forward': (_I32, [_VP, _I32, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP]),
+    'aninerf_render_workspace_bytes': (_I64, [_I64, _I32, _I32, _I64, _I64]),
+    'aninerf_render_rays': (_I32, [_VP, C.POINTER(Frame), C.POINTER(RenderParams), _VP, _VP, _VP, _VP, _VP, _VP, _I64,
+                                   C.POINTER(RenderOutputs), _VP, _I64, _VP]),
+    'aninerf_query_workspace_bytes': (_I64, [_I64, _I64]),
+    'aninerf_query_alpha': (_I32, [_VP, C.POINTER(Frame), _VP, _I64, _I64, _F, _I32, _I32, _VP, _VP, _VP, _I64, _VP]),
+}
+
+_lib = None
+
+
+class AninerfError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded shared library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                              f'or `make -C animatable_nerf_b200/csrc` -- there is no CPU fallback')
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise AninerfError(f'libaninerf_b200 error {rc}: {lib().aninerf_last_error().decode()}')
+
+
+def ptr(t):
+    """device (or host) data pointer of a tensor, None -> NULL"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """contiguous float32 view/copy on the same device"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise AninerfError(f'{name} must be a CUDA tensor: the B200 path has no CPU fallback')

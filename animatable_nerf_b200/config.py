@@ -1,0 +1,48 @@
+"""The cfg keys the render path reads (lib/config/config.py:9-137, configs/aninerf_s9p.yaml:58-72).
+
+Inside the reference tree the global `lib.config.cfg` is used as-is (drop-in); stand-alone (tests,
+bench) a plain namespace with the same key names and the aninerf_313 defaults is used.
+"""
+from __future__ import annotations
+
+import types
+
+DEFAULTS = dict(
+    N_samples=64, N_rand=1024, perturb=1.0, norm_th=0.05, train_th=0.0, white_bkgd=False, raw_noise_std=0,
+    xyz_res=10, view_res=4, box_padding=0.05, voxel_size=[0.005, 0.005, 0.005],
+    test_novel_pose=False, aninerf_animation=False, num_train_frame=60, num_eval_frame=1000,
+    # knobs of this implementation (unknown keys are legal in the reference's yacs fork)
+    b200_bw_precision=3,      # 3: bf16x3 split products (fp32-equivalent) / 1: single bf16 pass
+    b200_nerf_precision=1,
+    b200_render_only=False,   # True: skip the canonical tbw pass and the raw/pbw/tbw outputs
+)
+
+# configs/aninerf_313.yaml:23-29 and configs/aninerf_s9p.yaml:79-93
+PRESETS = {
+    'aninerf_313': dict(num_train_frame=60, num_eval_frame=1000),
+    'aninerf_s9p': dict(num_train_frame=260, num_eval_frame=133),
+}
+
+
+def make_cfg(preset: str = 'aninerf_313', **overrides):
+    d = dict(DEFAULTS)
+    d.update(PRESETS[preset])
+    d.update(overrides)
+    return types.SimpleNamespace(**d)
+
+
+def get(cfg, key):
+    """cfg.<key> with this package's default when the reference cfg does not define the key"""
+    try:
+        return getattr(cfg, key)
+    except (AttributeError, KeyError):
+        return DEFAULTS[key]
+
+
+def global_cfg():
+    """The reference's process-global cfg when running inside its tree, else the aninerf_313 defaults."""
+    try:
+        from lib.config import cfg   # noqa: the reference's own module
+        return cfg
+    except Exception:
+        return make_cfg()

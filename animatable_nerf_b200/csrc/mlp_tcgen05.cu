@@ -1,0 +1,901 @@
+// The two dense fields of the path -- the neural blend-weight MLP (tpose_nerf_network.py:55-77,
+// :304-315) and the canonical NeRF MLP (tpose_nerf_network.py:252-275) -- as ONE persistent,
+// warp-specialised tcgen05 kernel family for sm_100a.
+//
+// Per CTA (one per SM): a 128-sample tile lives in shared memory as the bf16 A operand of every
+// layer (K-major, no-swizzle core-matrix layout [K/8][128 rows][8]); weights stream from L2 through
+// a ring of 16 KB stages filled by bulk TMA copies (cp.async.bulk) of pre-packed operand images;
+// one elected thread issues tcgen05.mma (M=128, N<=256, K=16) into a 256-column fp32 TMEM
+// accumulator; four epilogue warps (thread == row == TMEM lane) read it back with tcgen05.ld,
+// apply bias+ReLU, re-quantise to bf16 (hi, and lo for the split-precision mode) and write the next
+// layer's A operand in place.  Positional encoding is generated in-kernel straight into the A
+// operand; the last epilogue is the field's head (softmax + inverse LBS, or alpha/rgb activation +
+// tbounds masking + scatter).
+//
+// Precision modes: NPASS=1 single bf16 product; NPASS=3 "bf16x3": x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+// with fp32 accumulation (fp32-equivalent; the blend-weight field needs it for the 1e-5 gate).
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace aninerf {
+
+// ------------------------------------------------------------------------------------------------
+// layout constants
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_M = 128;
+constexpr int CHUNK_BYTES = TILE_M * 16;     // one 8-wide K chunk of the A tile: 128 rows x 16 B
+constexpr int PE_CHUNK0 = 0;                 // A chunks 0..7   : PE(xyz) 63 + pad
+constexpr int HID_CHUNK0 = 8;                // A chunks 8..39  : hidden 256
+constexpr int VIEW_CHUNK0 = 40;              // A chunks 40..43 : PE(viewdir) 27 + pad (NeRF only)
+constexpr int STAGE_BYTES = 16384;
+constexpr int MAX_LAYERS = 9;
+constexpr int BIAS_FLOATS = MAX_LAYERS * 256;
+constexpr int SMEM_LIMIT = 232448;           // 227 KB
+
+struct Step {          // one weight-ring stage worth of MMAs
+  uint32_t w_off;      // byte offset of this step's operand image (hi, then lo) in the packed buffer
+  uint32_t bytes;      // bytes to copy (hi [+ lo])
+  uint16_t a_chunk;    // first A chunk consumed
+  uint16_t n_k16;      // K=16 MMAs (per pass) in this step
+  uint16_t layer;
+  uint16_t flags;      // 1: first step of its layer, 2: last step of its layer
+};
+
+struct LayerDev {
+  int32_t n_pad;       // MMA N (multiple of 16)
+  int32_t n_out;       // real outputs
+  int32_t relu;
+  int32_t bias_off;    // float offset of this layer's bias table inside `bias`
+  int32_t n_tables;
+};
+
+struct FieldDev {
+  const uint8_t *image;    // packed weights for this precision
+  const Step *steps;
+  int32_t n_steps;
+  int32_t n_layers;
+  LayerDev layers[MAX_LAYERS];
+  const float *bias;       // all bias tables
+  const float *head;       // NeRF: alpha_w[256], alpha_b, rgb_w[3][128], rgb_b[3]
+};
+
+struct MlpArgs {
+  FieldDev f;
+  int32_t latent_index;
+  const float *pts;        // (n,3)
+  const float *viewdir;    // (n,3) NeRF
+  int64_t n;
+  const int32_t *n_dev;
+  // BW head
+  const float *smpl_bw;    // (n,24) or null
+  const float *vol_w24;    // (X,Y,Z,24) or null
+  const float *grid_bounds;   // device (2,3)
+  int32_t grid_dim[3];
+  const float *A;          // (24,4,4) or null
+  float *bw_out;           // (n,24) or null
+  float *tpts_out;         // (n,3) or null
+  // NeRF head
+  float *sigma_out, *rgb_out;
+  const float *dists;
+  const float *tbounds;
+  const int32_t *index;
+  float *raw_out;
+  float *sigma_masked_out;
+  int32_t desc_swap;       // debug: swap LBO/SBO roles
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("aninerf mlp: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B contiguous;
+// lbo = byte stride between the two core matrices of one K=16 slice, sbo = stride between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// write 8 consecutive K elements of `row` (one 16-byte core-matrix row) into A chunk `chunk`
+template <int NPASS>
+__device__ __forceinline__ void store_chunk(uint8_t *a_hi, uint8_t *a_lo, int chunk, int row, const float (&x)[8]) {
+  uint4 h;
+  h.x = pack_bf16(x[0], x[1]);
+  h.y = pack_bf16(x[2], x[3]);
+  h.z = pack_bf16(x[4], x[5]);
+  h.w = pack_bf16(x[6], x[7]);
+  *reinterpret_cast<uint4 *>(a_hi + chunk * CHUNK_BYTES + row * 16) = h;
+  if (NPASS == 3) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = x[j] - bf16_round(x[j]);
+    uint4 l;
+    l.x = pack_bf16(r[0], r[1]);
+    l.y = pack_bf16(r[2], r[3]);
+    l.z = pack_bf16(r[4], r[5]);
+    l.w = pack_bf16(r[6], r[7]);
+    *reinterpret_cast<uint4 *>(a_lo + chunk * CHUNK_BYTES + row * 16) = l;
+  }
+}
+
+// NeRF positional encoding of a 3-vector (embedder.py:11-36): [x, sin(2^0 x), cos(2^0 x), ...], 3-wide blocks
+template <int NPASS, int L>
+__device__ __forceinline__ void write_pe(uint8_t *a_hi, uint8_t *a_lo, int chunk0, int row, float px, float py, float pz) {
+  constexpr int NV = 3 + 6 * L;                 // 63 or 27
+  constexpr int NCH = (NV + 7) / 8;             // 8 or 4
+  float v[NCH * 8];
+  v[0] = px;
+  v[1] = py;
+  v[2] = pz;
+  float p[3] = {px, py, pz};
+#pragma unroll
+  for (int f = 0; f < L; ++f) {
+    float fr = (float)(1 << f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(p[c] * fr, &s, &co);
+      v[3 + 6 * f + c] = s;
+      v[3 + 6 * f + 3 + c] = co;
+    }
+  }
+#pragma unroll
+  for (int j = NV; j < NCH * 8; ++j) v[j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = v[c * 8 + j];
+    store_chunk<NPASS>(a_hi, a_lo, chunk0 + c, row, x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int NPASS, bool NERF>
+struct Cfg {
+  static constexpr int A_CHUNKS = NERF ? 44 : 40;
+  static constexpr int A_BYTES = A_CHUNKS * CHUNK_BYTES;
+  static constexpr int A_TOTAL = A_BYTES * (NPASS == 3 ? 2 : 1);
+  static constexpr int HEAD_BYTES = NERF ? 2576 : 1152;
+  static constexpr int FIXED = A_TOTAL + BIAS_FLOATS * 4 + HEAD_BYTES + 256;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = FIXED + STAGES * STAGE_BYTES;
+  static_assert(STAGES >= 2, "weight ring needs at least two stages");
+  // offsets
+  static constexpr int OFF_A_HI = 0;
+  static constexpr int OFF_A_LO = A_BYTES;                      // only when NPASS == 3
+  static constexpr int OFF_RING = A_TOTAL;
+  static constexpr int OFF_BIAS = OFF_RING + STAGES * STAGE_BYTES;
+  static constexpr int OFF_HEAD = OFF_BIAS + BIAS_FLOATS * 4;
+  static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
+};
+
+constexpr int N_THREADS = 192;   // warps 0-3: rows / epilogue; warp 4: weight producer; warp 5: TMEM alloc + MMA issue
+
+template <int NPASS, bool NERF>
+__global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant__ MlpArgs args) {
+  using C = Cfg<NPASS, NERF>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *a_hi = smem + C::OFF_A_HI;
+  uint8_t *a_lo = smem + C::OFF_A_LO;
+  uint8_t *ring = smem + C::OFF_RING;
+  float *s_bias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
+  float *s_head = reinterpret_cast<float *>(smem + C::OFF_HEAD);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+  // barrier slots: [0..S) full, [S..2S) empty, 2S: a_ready, 2S+1: acc_ready
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = smem_u32(bars + C::STAGES);
+  const uint32_t bar_a_ready = smem_u32(bars + 2 * C::STAGES);
+  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + 1);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const FieldDev &F = args.f;
+  const int64_t n_valid = args.n_dev ? (int64_t)min((int64_t)*args.n_dev, args.n) : args.n;
+  const int64_t n_tiles = (n_valid + TILE_M - 1) / TILE_M;
+
+  // ---- one-time setup --------------------------------------------------------------------
+  for (int i = threadIdx.x; i < BIAS_FLOATS; i += N_THREADS) {
+    int l = i >> 8, j = i & 255;
+    float b = 0.f;
+    if (l < F.n_layers && j < F.layers[l].n_out) {
+      int t = min(max(args.latent_index, 0), F.layers[l].n_tables - 1);
+      b = F.bias[F.layers[l].bias_off + t * F.layers[l].n_out + j];
+    }
+    s_bias[i] = b;
+  }
+  if (NERF) {
+    for (int i = threadIdx.x; i < 644; i += N_THREADS) s_head[i] = F.head[i];
+  } else if (args.A) {
+    for (int i = threadIdx.x; i < 288; i += N_THREADS) s_head[i] = args.A[(i / 12) * 16 + (i % 12)];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_a_ready, TILE_M);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===== weight producer: stream the packed operand images through the ring =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < F.n_steps; ++s) {
+          Step st = F.steps[s];
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, st.bytes);
+          bulk_g2s(smem_u32(ring + stage * STAGE_BYTES), F.image + st.w_off, st.bytes, bar_full + 8 * stage);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer ===========================================================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      const uint32_t a_lbo = args.desc_swap ? 128u : (uint32_t)CHUNK_BYTES;
+      const uint32_t a_sbo = args.desc_swap ? (uint32_t)CHUNK_BYTES : 128u;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < F.n_steps; ++s) {
+          Step st = F.steps[s];
+          const int n_pad = F.layers[st.layer].n_pad;
+          const uint32_t idesc = instr_desc(n_pad);
+          const uint32_t b_k_stride = (uint32_t)n_pad * 16u;       // bytes between K core matrices in the image
+          const uint32_t b_lbo = args.desc_swap ? 128u : b_k_stride;
+          const uint32_t b_sbo = args.desc_swap ? b_k_stride : 128u;
+          if (st.flags & 1) {
+            mbar_wait(bar_a_ready, a_phase);   // A operand of this layer written, accumulator drained
+            a_phase ^= 1;
+          }
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(ring + stage * STAGE_BYTES);
+          const uint32_t b_lo = b_hi + (uint32_t)st.n_k16 * 2u * b_k_stride;
+          for (int k = 0; k < st.n_k16; ++k) {
+            const uint32_t a_off = (uint32_t)(st.a_chunk + 2 * k) * CHUNK_BYTES;
+            const uint64_t adh = smem_desc(smem_u32(a_hi) + a_off, a_lbo, a_sbo);
+            const uint64_t bdh = smem_desc(b_hi + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
+            const uint32_t fresh = ((st.flags & 1) && k == 0) ? 0u : 1u;
+            umma_bf16(tmem_base, adh, bdh, idesc, fresh);
+            if (NPASS == 3) {
+              const uint64_t adl = smem_desc(smem_u32(a_lo) + a_off, a_lbo, a_sbo);
+              const uint64_t bdl = smem_desc(b_lo + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
+              umma_bf16(tmem_base, adl, bdh, idesc, 1u);
+              umma_bf16(tmem_base, adh, bdl, idesc, 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);        // frees the ring stage once these MMAs retire
+          if (st.flags & 2) umma_commit(bar_acc);    // layer done: accumulator ready for the epilogue
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===== row threads: input encoding, per-layer epilogues, heads =============================
+    const int row = threadIdx.x;                       // == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t gi = tile * TILE_M + row;
+      const bool valid = gi < n_valid;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) {
+        px = __ldg(args.pts + 3 * gi);
+        py = __ldg(args.pts + 3 * gi + 1);
+        pz = __ldg(args.pts + 3 * gi + 2);
+      }
+      write_pe<NPASS, 10>(a_hi, a_lo, PE_CHUNK0, row, px, py, pz);
+      if (NERF) {
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        if (valid) {
+          vx = __ldg(args.viewdir + 3 * gi);
+          vy = __ldg(args.viewdir + 3 * gi + 1);
+          vz = __ldg(args.viewdir + 3 * gi + 2);
+        }
+        write_pe<NPASS, 4>(a_hi, a_lo, VIEW_CHUNK0, row, vx, vy, vz);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_a_ready);
+
+      float sigma = 0.f;   // NeRF: alpha_fc evaluated in fp32 inside the layer-7 epilogue
+      for (int l = 0; l < F.n_layers; ++l) {
+        const bool last = l == F.n_layers - 1;
+        float smpl[ANINERF_N_BONES];
+        if (!NERF && last) {
+          // initial SMPL weights of this row, fetched while the last layer's MMAs run
+#pragma unroll
+          for (int k = 0; k < ANINERF_N_BONES; ++k) smpl[k] = 0.f;
+          if (valid) {
+            if (args.smpl_bw) {
+              const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi * ANINERF_N_BONES);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) {
+                float4 t = __ldg(r4 + q);
+                smpl[4 * q] = t.x;
+                smpl[4 * q + 1] = t.y;
+                smpl[4 * q + 2] = t.z;
+                smpl[4 * q + 3] = t.w;
+              }
+            } else {
+              float w[8];
+              int off[8];
+              VolumeGrid vg;
+#pragma unroll
+              for (int a3 = 0; a3 < 3; ++a3) {
+                vg.lo[a3] = __ldg(args.grid_bounds + a3);
+                vg.ext[a3] = __fsub_rn(__ldg(args.grid_bounds + 3 + a3), vg.lo[a3]);
+                vg.dim[a3] = args.grid_dim[a3];
+              }
+              trilinear_corners(vg, px, py, pz, w, off);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                if (off[c] >= 0) {
+                  const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)off[c] * ANINERF_N_BONES);
+#pragma unroll
+                  for (int q = 0; q < 6; ++q) {
+                    float4 t = __ldg(r4 + q);
+                    smpl[4 * q] = __fadd_rn(smpl[4 * q], __fmul_rn(t.x, w[c]));
+                    smpl[4 * q + 1] = __fadd_rn(smpl[4 * q + 1], __fmul_rn(t.y, w[c]));
+                    smpl[4 * q + 2] = __fadd_rn(smpl[4 * q + 2], __fmul_rn(t.z, w[c]));
+                    smpl[4 * q + 3] = __fadd_rn(smpl[4 * q + 3], __fmul_rn(t.w, w[c]));
+                  }
+                }
+              }
+            }
+          }
+        }
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const float *bias = s_bias + l * 256;
+        const int n_pad = F.layers[l].n_pad;
+        if (!last) {
+          // hidden layer: bias + ReLU -> bf16 (hi/lo) -> A chunks 8..39 in place
+          const bool alpha_layer = NERF && (l == F.n_layers - 2);
+          for (int g = 0; g < n_pad / 32; ++g) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + g * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float x[8];
+              const float4 b0 = *reinterpret_cast<const float4 *>(bias + g * 32 + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4 *>(bias + g * 32 + q * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
+              if (alpha_layer) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8 + 4);
+                sigma = fmaf(x[0], w0.x, sigma);
+                sigma = fmaf(x[1], w0.y, sigma);
+                sigma = fmaf(x[2], w0.z, sigma);
+                sigma = fmaf(x[3], w0.w, sigma);
+                sigma = fmaf(x[4], w1.x, sigma);
+                sigma = fmaf(x[5], w1.y, sigma);
+                sigma = fmaf(x[6], w1.z, sigma);
+                sigma = fmaf(x[7], w1.w, sigma);
+              }
+              store_chunk<NPASS>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(bar_a_ready);
+        } else if (!NERF) {
+          // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
+          uint32_t v[32];
+          tmem_ld32(t_lane, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          float bw[ANINERF_N_BONES];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < ANINERF_N_BONES; ++k) {
+            bw[k] = logf(smpl[k] + 1e-9f) + (__uint_as_float(v[k]) + bias[k]);
+            mx = fmaxf(mx, bw[k]);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < ANINERF_N_BONES; ++k) {
+            bw[k] = expf(bw[k] - mx);
+            sum += bw[k];
+          }
+          const float inv_sum = 1.0f / sum;
+#pragma unroll
+          for (int k = 0; k < ANINERF_N_BONES; ++k) bw[k] *= inv_sum;
+          if (valid) {
+            if (args.bw_out) {
+              float4 *o4 = reinterpret_cast<float4 *>(args.bw_out + gi * ANINERF_N_BONES);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) o4[q] = make_float4(bw[4 * q], bw[4 * q + 1], bw[4 * q + 2], bw[4 * q + 3]);
+            }
+            if (args.tpts_out) {
+              float M[12];
+#pragma unroll
+              for (int j = 0; j < 12; ++j) M[j] = 0.f;
+#pragma unroll
+              for (int k = 0; k < ANINERF_N_BONES; ++k)
+#pragma unroll
+                for (int j = 0; j < 12; ++j) M[j] = fmaf(bw[k], s_head[k * 12 + j], M[j]);
+              float qx = px - M[3], qy = py - M[7], qz = pz - M[11];
+              float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], kk = M[10];
+              float c00 = e * kk - f * h, c01 = c * h - b * kk, c02 = b * f - c * e;
+              float c10 = f * g - d * kk, c11 = a * kk - c * g, c12 = c * d - a * f;
+              float c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+              float inv = 1.0f / (a * c00 + b * c10 + c * c20);
+              args.tpts_out[3 * gi] = (c00 * qx + c01 * qy + c02 * qz) * inv;
+              args.tpts_out[3 * gi + 1] = (c10 * qx + c11 * qy + c12 * qz) * inv;
+              args.tpts_out[3 * gi + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
+            }
+          }
+        } else {
+          // ---- NeRF head: view layer (ReLU) -> rgb_fc in fp32; alpha from the layer-7 epilogue ---
+          float rgb[3] = {s_head[257 + 384], s_head[257 + 385], s_head[257 + 386]};
+          for (int g = 0; g < n_pad / 32; ++g) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + g * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = fmaxf(__uint_as_float(v[j]) + bias[g * 32 + j], 0.f);
+              rgb[0] = fmaf(x, s_head[257 + g * 32 + j], rgb[0]);
+              rgb[1] = fmaf(x, s_head[257 + 128 + g * 32 + j], rgb[1]);
+              rgb[2] = fmaf(x, s_head[257 + 256 + g * 32 + j], rgb[2]);
+            }
+          }
+          tc_fence_before();
+          sigma += s_head[256];
+          if (valid) {
+            if (args.sigma_out) args.sigma_out[gi] = sigma;
+            if (args.rgb_out) {
+              args.rgb_out[3 * gi] = rgb[0];
+              args.rgb_out[3 * gi + 1] = rgb[1];
+              args.rgb_out[3 * gi + 2] = rgb[2];
+            }
+            if (args.raw_out) {
+              // tail of Network.forward (tpose_nerf_network.py:186-212)
+              bool inside = px > args.tbounds[0] && px < args.tbounds[3] && py > args.tbounds[1] && py < args.tbounds[4] &&
+                            pz > args.tbounds[2] && pz < args.tbounds[5];
+              float sg = inside ? sigma : 0.f;
+              if (args.sigma_masked_out) args.sigma_masked_out[gi] = sg;
+              float al = 1.0f - expf(-fmaxf(sg, 0.f) * __ldg(args.dists + gi));
+              float4 o = make_float4(1.0f / (1.0f + expf(-rgb[0])), 1.0f / (1.0f + expf(-rgb[1])), 1.0f / (1.0f + expf(-rgb[2])), al);
+              reinterpret_cast<float4 *>(args.raw_out)[__ldg(args.index + gi)] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown --------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: packing and the net object
+// ------------------------------------------------------------------------------------------------
+static inline uint16_t f2bf(float f) {   // round to nearest even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct Segment { int src0, len, pad; };   // source columns [src0, src0+len) zero-padded to `pad`
+
+struct HostLayer {
+  int n_out, n_pad, k_in, k_pad, a_chunk0, relu, n_tables;
+  std::vector<Segment> segs;
+};
+
+struct FieldImage {          // per (field, precision)
+  uint8_t *image = nullptr;
+  Step *steps = nullptr;
+  int n_steps = 0;
+};
+
+struct FieldHost {
+  bool loaded = false;
+  int n_layers = 0;
+  LayerDev layers[MAX_LAYERS];
+  float *bias = nullptr;
+  float *head = nullptr;
+  FieldImage img[2];         // [0]: NPASS=1, [1]: NPASS=3
+};
+
+}  // namespace aninerf
+
+struct aninerf_net {
+  aninerf::FieldHost fields[ANINERF_N_FIELDS];
+};
+
+namespace aninerf {
+
+static void free_field(FieldHost &f) {
+  cudaFree(f.bias);
+  cudaFree(f.head);
+  for (auto &im : f.img) {
+    cudaFree(im.image);
+    cudaFree(im.steps);
+    im = FieldImage();
+  }
+  f = FieldHost();
+}
+
+// architecture tables (tpose_nerf_network.py:12-38, 219-239, 279-294 after folding)
+static int describe_layers(int field, const aninerf_layer *L, int n_layers, std::vector<HostLayer> &out) {
+  const bool nerf = field == ANINERF_FIELD_NERF;
+  if (n_layers != 9) return fail(ANINERF_EINVAL, "%s: a field has 9 dense layers after folding%s", "aninerf_net_load_field");
+  for (int l = 0; l < 9; ++l) {
+    HostLayer h;
+    h.n_out = L[l].n_out;
+    h.k_in = L[l].k_in;
+    h.relu = L[l].relu;
+    h.n_tables = L[l].n_tables;
+    int want_k, want_n;
+    if (l == 0) {
+      want_k = 63; want_n = 256; h.segs = {{0, 63, 64}}; h.a_chunk0 = PE_CHUNK0;
+    } else if (l == 5) {
+      want_k = 63 + 256; want_n = 256; h.segs = {{0, 63, 64}, {63, 256, 256}}; h.a_chunk0 = PE_CHUNK0;
+    } else if (l < 8) {
+      want_k = 256; want_n = 256; h.segs = {{0, 256, 256}}; h.a_chunk0 = HID_CHUNK0;
+    } else if (nerf) {
+      want_k = 256 + 27; want_n = 128; h.segs = {{0, 256, 256}, {256, 27, 32}}; h.a_chunk0 = HID_CHUNK0;
+    } else {
+      want_k = 256; want_n = ANINERF_N_BONES; h.segs = {{0, 256, 256}}; h.a_chunk0 = HID_CHUNK0;
+    }
+    if (h.k_in != want_k || h.n_out != want_n || !L[l].W || !L[l].bias_table || h.n_tables < 1)
+      return fail(ANINERF_EINVAL, "%s: layer shape does not match the aninerf architecture%s", "aninerf_net_load_field");
+    h.n_pad = (h.n_out + 31) / 32 * 32;
+    h.k_pad = 0;
+    for (auto &s : h.segs) h.k_pad += s.pad;
+    out.push_back(h);
+  }
+  return ANINERF_OK;
+}
+
+static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, int npass, FieldImage &im, cudaStream_t st) {
+  const int hi_max = npass == 3 ? STAGE_BYTES / 2 : STAGE_BYTES;
+  std::vector<Step> steps;
+  std::vector<uint8_t> image;
+  for (size_t l = 0; l < H.size(); ++l) {
+    const HostLayer &h = H[l];
+    // padded-K -> source column map
+    std::vector<int> col(h.k_pad, -1);
+    int kp = 0;
+    for (auto &s : h.segs) {
+      for (int j = 0; j < s.len; ++j) col[kp + j] = s.src0 + j;
+      kp += s.pad;
+    }
+    const int k16_total = h.k_pad / 16;
+    const int per_step = std::max(1, hi_max / (h.n_pad * 32));
+    for (int k0 = 0; k0 < k16_total; k0 += per_step) {
+      const int nk = std::min(per_step, k16_total - k0);
+      Step s;
+      s.w_off = (uint32_t)image.size();
+      const size_t hi_bytes = (size_t)nk * 2 * h.n_pad * 16;
+      s.bytes = (uint32_t)(hi_bytes * (npass == 3 ? 2 : 1));
+      s.a_chunk = (uint16_t)(h.a_chunk0 + 2 * k0);
+      s.n_k16 = (uint16_t)nk;
+      s.layer = (uint16_t)l;
+      s.flags = (uint16_t)((k0 == 0 ? 1 : 0) | (k0 + nk >= k16_total ? 2 : 0));
+      image.resize(image.size() + s.bytes, 0);
+      uint16_t *hi = reinterpret_cast<uint16_t *>(image.data() + s.w_off);
+      uint16_t *lo = reinterpret_cast<uint16_t *>(image.data() + s.w_off + hi_bytes);
+      for (int c = 0; c < nk * 2; ++c)          // 8-wide K chunk
+        for (int n = 0; n < h.n_pad; ++n)
+          for (int j = 0; j < 8; ++j) {
+            int k = (k0 * 2 + c) * 8 + j;
+            float w = 0.f;
+            if (n < h.n_out && col[k] >= 0) w = L[l].W[(size_t)n * h.k_in + col[k]];
+            uint16_t wh = f2bf(w);
+            size_t o = ((size_t)c * h.n_pad + n) * 8 + j;
+            hi[o] = wh;
+            if (npass == 3) lo[o] = f2bf(w - bf2f(wh));
+          }
+      steps.push_back(s);
+    }
+  }
+  for (auto &s : steps)
+    if (s.bytes > (uint32_t)STAGE_BYTES || (s.bytes & 15u)) return fail(ANINERF_EINVAL, "%s: internal: bad step size%s", __func__);
+  ANI_CUDA(cudaMalloc(&im.image, image.size()));
+  ANI_CUDA(cudaMalloc(&im.steps, steps.size() * sizeof(Step)));
+  ANI_CUDA(cudaMemcpyAsync(im.image, image.data(), image.size(), cudaMemcpyHostToDevice, st));
+  ANI_CUDA(cudaMemcpyAsync(im.steps, steps.data(), steps.size() * sizeof(Step), cudaMemcpyHostToDevice, st));
+  ANI_CUDA(cudaStreamSynchronize(st));   // the std::vectors go out of scope
+  im.n_steps = (int)steps.size();
+  return ANINERF_OK;
+}
+
+template <int NPASS, bool NERF>
+static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
+  using C = Cfg<NPASS, NERF>;
+  static bool configured = false;
+  if (!configured) {
+    ANI_CUDA(cudaFuncSetAttribute(mlp_kernel<NPASS, NERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  int64_t tiles = (a.n + TILE_M - 1) / TILE_M;
+  int grid = (int)std::min<int64_t>(tiles, sm_count());
+  if (grid <= 0) return ANINERF_OK;
+  mlp_kernel<NPASS, NERF><<<grid, N_THREADS, C::SMEM, st>>>(a);
+  ANI_LAUNCHED();
+  return ANINERF_OK;
+}
+
+static int desc_swap_flag() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ANINERF_DESC_SWAP");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs &a) {
+  if (!net) return fail(ANINERF_EINVAL, "%s: null net%s", __func__);
+  if (field < 0 || field >= ANINERF_N_FIELDS) return fail(ANINERF_EINVAL, "%s: bad field%s", __func__);
+  if (precision != 1 && precision != 3) return fail(ANINERF_EINVAL, "%s: precision must be 1 or 3%s", __func__);
+  const FieldHost &f = net->fields[field];
+  if (!f.loaded) return fail(ANINERF_ESTATE, "%s: field weights not loaded%s", __func__);
+  const FieldImage &im = f.img[precision == 3 ? 1 : 0];
+  a.f.image = im.image;
+  a.f.steps = im.steps;
+  a.f.n_steps = im.n_steps;
+  a.f.n_layers = f.n_layers;
+  memcpy(a.f.layers, f.layers, sizeof(f.layers));
+  a.f.bias = f.bias;
+  a.f.head = f.head;
+  a.desc_swap = desc_swap_flag();
+  return ANINERF_OK;
+}
+
+// internal C++ entry points shared with render.cu
+int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *pts, const float *smpl_bw, const float *vol_w24,
+                    const int32_t dims[3], const float *bounds, int64_t n, const int32_t *n_dev, const float *A, float *bw_out,
+                    float *tpts_out, int precision, cudaStream_t st) {
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_field(net, field, precision, a);
+  if (rc) return rc;
+  a.latent_index = latent_index;
+  a.pts = pts;
+  a.n = n;
+  a.n_dev = n_dev;
+  a.smpl_bw = smpl_bw;
+  a.vol_w24 = vol_w24;
+  if (!smpl_bw) {
+    a.grid_bounds = bounds;
+    for (int k = 0; k < 3; ++k) a.grid_dim[k] = dims[k];
+  }
+  a.A = A;
+  a.bw_out = bw_out;
+  a.tpts_out = tpts_out;
+  return precision == 3 ? launch_mlp<3, false>(a, st) : launch_mlp<1, false>(a, st);
+}
+
+int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
+                      float *sigma_out, float *rgb_out, const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
+                      float *sigma_masked_out, int precision, cudaStream_t st) {
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_field(net, ANINERF_FIELD_NERF, precision, a);
+  if (rc) return rc;
+  a.latent_index = latent_index;
+  a.pts = pts;
+  a.viewdir = viewdir;
+  a.n = n;
+  a.n_dev = n_dev;
+  a.sigma_out = sigma_out;
+  a.rgb_out = rgb_out;
+  a.dists = dists;
+  a.tbounds = tbounds;
+  a.index = index;
+  a.raw_out = raw_out;
+  a.sigma_masked_out = sigma_masked_out;
+  return precision == 3 ? launch_mlp<3, true>(a, st) : launch_mlp<1, true>(a, st);
+}
+
+}  // namespace aninerf
+
+using namespace aninerf;
+
+extern "C" {
+
+int aninerf_net_create(aninerf_net **out) {
+  ANI_CHECK_ARG(out);
+  *out = new aninerf_net();
+  return ANINERF_OK;
+}
+
+int aninerf_net_destroy(aninerf_net *net) {
+  if (!net) return ANINERF_OK;
+  for (auto &f : net->fields) free_field(f);
+  delete net;
+  return ANINERF_OK;
+}
+
+int aninerf_net_load_field(aninerf_net *net, int32_t field, const aninerf_layer *layers, int32_t n_layers, const float *alpha_w,
+                           const float *alpha_b, const float *rgb_w, const float *rgb_b, void *stream) {
+  ANI_CHECK_ARG(net && layers && field >= 0 && field < ANINERF_N_FIELDS);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool nerf = field == ANINERF_FIELD_NERF;
+  if (nerf) ANI_CHECK_ARG(alpha_w && alpha_b && rgb_w && rgb_b);
+  std::vector<HostLayer> H;
+  int rc = describe_layers(field, layers, n_layers, H);
+  if (rc) return rc;
+  FieldHost &f = net->fields[field];
+  ANI_CUDA(cudaStreamSynchronize(st));   // nothing may still be reading the old images
+  free_field(f);
+  f.n_layers = n_layers;
+  // bias tables
+  std::vector<float> bias;
+  for (int l = 0; l < n_layers; ++l) {
+    f.layers[l].n_pad = H[l].n_pad;
+    f.layers[l].n_out = H[l].n_out;
+    f.layers[l].relu = H[l].relu;
+    f.layers[l].bias_off = (int)bias.size();
+    f.layers[l].n_tables = H[l].n_tables;
+    bias.insert(bias.end(), layers[l].bias_table, layers[l].bias_table + (size_t)H[l].n_tables * H[l].n_out);
+  }
+  ANI_CUDA(cudaMalloc(&f.bias, bias.size() * 4));
+  ANI_CUDA(cudaMemcpyAsync(f.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, st));
+  if (nerf) {
+    std::vector<float> head(644, 0.f);
+    memcpy(head.data(), alpha_w, 256 * 4);
+    head[256] = alpha_b[0];
+    memcpy(head.data() + 257, rgb_w, 384 * 4);
+    memcpy(head.data() + 257 + 384, rgb_b, 3 * 4);
+    ANI_CUDA(cudaMalloc(&f.head, head.size() * 4));
+    ANI_CUDA(cudaMemcpyAsync(f.head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, st));
+    ANI_CUDA(cudaStreamSynchronize(st));
+  }
+  ANI_CUDA(cudaStreamSynchronize(st));
+  rc = build_image(layers, H, 1, f.img[0], st);
+  if (rc) return rc;
+  rc = build_image(layers, H, 3, f.img[1], st);
+  if (rc) return rc;
+  f.loaded = true;
+  return ANINERF_OK;
+}
+
+int aninerf_bw_forward(aninerf_net *net, int32_t field, int32_t latent_index, const float *pts, const float *smpl_bw, int64_t n,
+                       const int32_t *n_dev, const float *A, float *bw_out, float *tpts_out, int32_t precision, void *stream) {
+  ANI_CHECK_ARG(net && pts && smpl_bw && n >= 0 && (field == ANINERF_FIELD_BW || field == ANINERF_FIELD_NOVEL_BW));
+  ANI_CHECK_ARG(!tpts_out || A);
+  if (n == 0) return ANINERF_OK;
+  return bw_forward_impl(net, field, latent_index, pts, smpl_bw, nullptr, nullptr, nullptr, n, n_dev, A, bw_out, tpts_out, precision,
+                         (cudaStream_t)stream);
+}
+
+int aninerf_nerf_forward(aninerf_net *net, int32_t latent_index, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
+                         float *sigma_out, float *rgb_out, const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
+                         float *sigma_masked_out, int32_t precision, void *stream) {
+  ANI_CHECK_ARG(net && pts && viewdir && n >= 0);
+  ANI_CHECK_ARG(!raw_out || (dists && tbounds && index));
+  if (n == 0) return ANINERF_OK;
+  return nerf_forward_impl(net, latent_index, pts, viewdir, n, n_dev, sigma_out, rgb_out, dists, tbounds, index, raw_out, sigma_masked_out,
+                           precision, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""Drop-in `Renderer` for `lib/networks/renderer/tpose_renderer.py` (select it with
+`renderer_module` / `renderer_path`).
+
+`Renderer(net).render(batch)` keeps the reference contract (tpose_renderer.py:159-186): the batch
+schema of `lib/datasets/tpose_dataset.py`:236-277 in, a dict with `rgb_map (1,R,3)`, `acc_map (1,R)`,
+`depth_map (1,R)`, `raw (1,R*S,4)`, `pbw`/`tbw (1,n'',24)` out, CPU tensors when no gradient is
+required.  The whole frame goes through ONE call of the fused C-ABI entry `aninerf_render_rays`;
+the reference's 2048-ray chunk loop survives only as the semantic unit of the per-chunk
+argmin / argmax forcing (tpose_nerf_network.py:154, :193-194).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, config
+from .tpose_nerf_network import _frame_struct
+
+
+def select_forced_argmax(sigma_masked: torch.Tensor, chunk_offsets: torch.Tensor, train_th: float) -> torch.Tensor:
+    """alpha_ind of tpose_nerf_network.py:192-194 for all chunks at once: sigma > train_th, plus the
+    first arg-max row of every chunk.  sigma_masked (n',), chunk_offsets (n_chunks+1,) -> bool (n',)."""
+    n = sigma_masked.numel()
+    sel = sigma_masked > train_th
+    counts = (chunk_offsets[1:] - chunk_offsets[:-1]).long()
+    n_chunks = counts.numel()
+    chunk_id = torch.repeat_interleave(torch.arange(n_chunks, device=sigma_masked.device), counts, output_size=n)
+    cmax = torch.full((n_chunks,), float('-inf'), device=sigma_masked.device).scatter_reduce(0, chunk_id, sigma_masked, 'amax')
+    rows = torch.arange(n, device=sigma_masked.device)
+    cand = torch.where(sigma_masked == cmax[chunk_id], rows, torch.full_like(rows, n))
+    first = torch.full((n_chunks,), n, dtype=rows.dtype, device=rows.device).scatter_reduce(0, chunk_id, cand, 'amin')
+    sel[first[first < n]] = True
+    return sel
+
+
+class Renderer:
+    def __init__(self, net, cfg=None):
+        self.net = net
+        self.cfg = cfg if cfg is not None else getattr(net, 'cfg', None) or config.global_cfg()
+        self._ws = None
+        self._t_vals = {}
+
+    # ---------------------------------------------------------------------------------------
+    def _workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _tv(self, S, device):
+        key = (S, device)
+        if key not in self._t_vals:
+            # torch.linspace on the CPU, as tpose_renderer.py:26 computes it (not bit-equal to i/(S-1))
+            self._t_vals[key] = torch.linspace(0., 1., steps=S).to(device)
+        return self._t_vals[key]
+
+    # ---------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def render_device(self, batch, t_rand=None, want_bw=None):
+        """The fused path, results left on the device.  Returns a dict with rgb_map/acc_map/depth_map
+        (and raw, n_active, pbw_all/tbw_all/sigma_masked/chunk_offsets when want_bw)."""
+        cfg = self.cfg
+        ray_o, ray_d = batch['ray_o'], batch['ray_d']
+        _lib.require_cuda(ray_o, "batch['ray_o']")
+        dev = ray_o.device
+        R = ray_o.shape[1]
+        S = int(config.get(cfg, 'N_samples'))
+        if want_bw is None:
+            want_bw = not bool(config.get(cfg, 'b200_render_only'))
+        o, d = _lib.f32c(ray_o.reshape(-1, 3)), _lib.f32c(ray_d.reshape(-1, 3))
+        near, far = _lib.f32c(batch['near'].reshape(-1)), _lib.f32c(batch['far'].reshape(-1))
+        fr, keep = _frame_struct(batch, need_tbw=want_bw)
+        pr = _lib.RenderParams(n_samples=S, chunk_rays=_lib.CHUNK_RAYS, norm_th=float(config.get(cfg, 'norm_th')),
+                               white_bkgd=int(bool(config.get(cfg, 'white_bkgd'))),
+                               novel_pose=int(bool(config.get(cfg, 'test_novel_pose'))), want_bw=int(want_bw),
+                               bw_precision=int(config.get(cfg, 'b200_bw_precision')),
+                               nerf_precision=int(config.get(cfg, 'b200_nerf_precision')))
+        n = R * S
+        n_chunks = (R + _lib.CHUNK_RAYS - 1) // _lib.CHUNK_RAYS
+        out = {
+            'rgb_map': torch.empty(R, 3, device=dev), 'acc_map': torch.empty(R, device=dev), 'depth_map': torch.empty(R, device=dev),
+            'raw': torch.empty(n, 4, device=dev), 'n_active': torch.zeros(1, dtype=torch.int32, device=dev),
+            'chunk_offsets': torch.zeros(n_chunks + 1, dtype=torch.int32, device=dev),
+        }
+        if want_bw:
+            out['pbw_all'] = torch.empty(n, 24, device=dev)
+            out['tbw_all'] = torch.empty(n, 24, device=dev)
+            out['sigma_masked'] = torch.empty(n, device=dev)
+            out['active_index'] = torch.empty(n, dtype=torch.int32, device=dev)
+        ro = _lib.RenderOutputs()
+        for k in ('rgb_map', 'acc_map', 'depth_map', 'raw', 'pbw_all', 'tbw_all', 'sigma_masked', 'active_index', 'n_active',
+                  'chunk_offsets'):
+            setattr(ro, k, out[k].data_ptr() if k in out else None)
+        pv = int(fr.pbw_dims[0]) * fr.pbw_dims[1] * fr.pbw_dims[2]
+        tv = int(fr.tbw_dims[0]) * fr.tbw_dims[1] * fr.tbw_dims[2] if want_bw else 0
+        ws_bytes = _lib.lib().aninerf_render_workspace_bytes(R, S, int(want_bw), pv, tv)
+        ws = self._workspace(ws_bytes, dev)
+        tr = _lib.f32c(t_rand.reshape(R, S)) if t_rand is not None else None
+        _lib.check(_lib.lib().aninerf_render_rays(self.net.packed().handle, C.byref(fr), C.byref(pr), _lib.ptr(o), _lib.ptr(d),
+                                                  _lib.ptr(near), _lib.ptr(far), _lib.ptr(self._tv(S, dev)), _lib.ptr(tr), R,
+                                                  C.byref(ro), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+        out['_keep'] = (keep, o, d, near, far, tr)
+        return out
+
+    @torch.no_grad()
+    def render(self, batch):
+        cfg = self.cfg
+        ray_o = batch['ray_o']
+        R = ray_o.shape[1]
+        S = int(config.get(cfg, 'N_samples'))
+        t_rand = None
+        if config.get(cfg, 'perturb') > 0. and self.net.training:
+            # the reference draws the jitter on the CPU generator (tpose_renderer.py:35)
+            t_rand = torch.rand(1, R, S).to(ray_o.device)
+        render_only = bool(config.get(cfg, 'b200_render_only'))
+        out = self.render_device(batch, t_rand=t_rand, want_bw=not render_only)
+        ret = {'rgb_map': out['rgb_map'].view(1, R, 3), 'acc_map': out['acc_map'].view(1, R), 'depth_map': out['depth_map'].view(1, R)}
+        if not render_only:
+            n_active = int(out['n_active'].item())
+            sel = select_forced_argmax(out['sigma_masked'][:n_active], out['chunk_offsets'], float(config.get(cfg, 'train_th')))
+            ret['raw'] = out['raw'].view(1, R * S, 4)
+            ret['pbw'] = out['pbw_all'][:n_active][sel].view(1, -1, 24)
+            ret['tbw'] = out['tbw_all'][:n_active][sel].view(1, -1, 24)
+        # tpose_renderer.py:154-155: outputs go to the host when no gradient is attached (always, this round)
+        return {k: v.detach().cpu() for k, v in ret.items()}

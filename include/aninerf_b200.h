@@ -1,0 +1,242 @@
+/*
+ * aninerf_b200.h -- C ABI of libaninerf_b200.so: the B200 (sm_100a) implementation of
+ * Animatable NeRF's per-ray render hot path.
+ *
+ * The reference (xx-peach/animatable_nerf) has no FFI layer: the seam is duck-typed Python
+ * (`Renderer.render(batch)`, `Network.*`).  Each entry point below names the reference
+ * function (file:line under /root/reference) whose arithmetic it replaces; the Python mirror of
+ * the reference interface (animatable_nerf_b200/tpose_renderer.py, tpose_nerf_network.py) binds
+ * these with ctypes.  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - the caller owns all memory (inputs, outputs, workspace); the library allocates only the
+ *    packed network weights held by an `aninerf_net` object;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises
+ *    the device and never throws; it returns 0 on success or a negative ANINERF_E* code, with a
+ *    message available from aninerf_last_error() (thread local);
+ *  - point arrays are point-major: xyz (n,3), blend weights (n,24|25), raw (n,4);
+ *  - float means IEEE fp32; "bit-exact" stages use round-to-nearest intrinsics in a fixed order.
+ */
+#ifndef ANINERF_B200_H
+#define ANINERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANINERF_ABI_VERSION 1
+#define ANINERF_N_BONES 24
+#define ANINERF_BW_CH 25          /* 24 skinning weights + distance-to-surface channel */
+#define ANINERF_MAX_SAMPLES 64    /* cfg.N_samples of every aninerf config (configs/aninerf_s9p.yaml:58) */
+#define ANINERF_CHUNK_RAYS 2048   /* tpose_renderer.py:170 -- a semantic unit (per-chunk argmin forcing) */
+
+enum {
+  ANINERF_OK = 0,
+  ANINERF_EINVAL = -1,    /* bad argument */
+  ANINERF_ECUDA = -2,     /* a CUDA runtime call failed */
+  ANINERF_ENOMEM = -3,    /* workspace too small / allocation failed */
+  ANINERF_ESTATE = -4     /* weights not loaded etc. */
+};
+
+int aninerf_version(void);
+const char *aninerf_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1: rays and SMPL-box intersection (fp64 arithmetic, bit-exact targets)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Camera: world->camera rotation R (row major), translation T, and inv(K) (row major), fp64. */
+typedef struct {
+  double Kinv[9];
+  double R[9];
+  double T[3];
+  int32_t H, W;
+} aninerf_camera;
+
+/* get_rays, lib/utils/if_nerf/if_nerf_data_utils.py:64-89, followed by the float32 cast of its
+ * callers (:328-329).  ray_o, ray_d: (H*W,3) fp32. */
+int aninerf_gen_rays(const aninerf_camera *cam_host, float *ray_o, float *ray_d, void *stream);
+
+/* get_near_far, if_nerf_data_utils.py:156-196.  bounds_host: (2,3) fp32 on the HOST.
+ * near/far: (n,) fp32 written for EVERY ray (0 where mask==0); mask: (n,) uint8. */
+int aninerf_near_far(const float *bounds_host, const float *ray_o, const float *ray_d, int64_t n,
+                     float *near, float *far, uint8_t *mask, void *stream);
+
+/* Stable compaction of rays by mask (the boolean indexing of get_rays_within_bounds,
+ * if_nerf_data_utils.py:334-336).  Outputs hold up to n rows; *count (device int32) receives the
+ * number kept.  workspace: aninerf_compact_workspace_bytes(n) bytes. */
+int64_t aninerf_compact_workspace_bytes(int64_t n);
+int aninerf_compact_rays(const float *ray_o, const float *ray_d, const float *near, const float *far,
+                         const uint8_t *mask, int64_t n, float *ray_o_out, float *ray_d_out,
+                         float *near_out, float *far_out, int32_t *index_out, int32_t *count,
+                         void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1b: stratified sample points, Renderer.get_wsampling_points + get_density_color,
+ * lib/networks/renderer/tpose_renderer.py:14-69
+ * ---------------------------------------------------------------------------------------- */
+/* t_vals: (S,) fp32 = torch.linspace(0,1,S) (passed in: it is not i/(S-1) rounded).
+ * t_rand: (n_rays,S) fp32 or NULL (cfg.perturb jitter, drawn by the caller on the host RNG as
+ * the reference does, tpose_renderer.py:35).  Any output pointer may be NULL.
+ * pts (n_rays*S,3), z_vals (n_rays,S), dists (n_rays*S,) [last interval duplicated, :64-65]. */
+int aninerf_sample_points(const float *ray_o, const float *ray_d, const float *near, const float *far,
+                          const float *t_vals, const float *t_rand, int64_t n_rays, int32_t n_samples,
+                          float *pts, float *z_vals, float *dists, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2: inverse linear-blend skinning pieces, lib/utils/blend_utils.py
+ * ---------------------------------------------------------------------------------------- */
+/* world_points_to_pose_points, blend_utils.py:6-16: (p - Th) @ R.  R (3,3), Th (3,). */
+int aninerf_world_to_pose(const float *wpts, int64_t n, const float *R, const float *Th, float *ppts,
+                          void *stream);
+
+/* pts_sample_blend_weights, blend_utils.py:119-149 (F.grid_sample trilinear / border /
+ * align_corners=True over a channels-last volume).  vol: (X,Y,Z,25) fp32 exactly as the reference
+ * batch holds it; bounds: (2,3).  out: (n,25) point-major (the reference returns (1,25,n)). */
+int aninerf_sample_blend_weights(const float *pts, int64_t n, const float *vol, const int32_t dims_host[3],
+                                 const float *bounds, float *out, void *stream);
+
+/* pose_points_to_tpose_points, blend_utils.py:41-59 (inverse LBS) and tpose_points_to_pose_points,
+ * blend_utils.py:77-90 (forward LBS).  bw: (n,24) point-major; A: (24,4,4). */
+int aninerf_inverse_lbs(const float *ppts, const float *bw, int64_t n, const float *A, float *tpts, void *stream);
+int aninerf_forward_lbs(const float *tpts, const float *bw, int64_t n, const float *A, float *ppts, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 5: alpha compositing, raw2outputs, lib/networks/renderer/nerf_net_utils.py:6-36
+ * ---------------------------------------------------------------------------------------- */
+/* raw: (n_rays,S,4) = (r,g,b,alpha) already activated; z_vals: (n_rays,S).
+ * rgb_map (n_rays,3), acc_map, depth_map, disp_map (n_rays,), weights (n_rays,S): any may be NULL. */
+int aninerf_composite(const float *raw, const float *z_vals, int64_t n_rays, int32_t n_samples,
+                      int32_t white_bkgd, float *rgb_map, float *acc_map, float *depth_map,
+                      float *disp_map, float *weights, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stages 3+4: the two MLPs on tcgen05 tensor cores
+ * ---------------------------------------------------------------------------------------- */
+typedef struct aninerf_net aninerf_net;   /* opaque: packed weights of one Network on one device */
+
+enum { ANINERF_FIELD_BW = 0, ANINERF_FIELD_NOVEL_BW = 1, ANINERF_FIELD_NERF = 2, ANINERF_N_FIELDS = 3 };
+
+int aninerf_net_create(aninerf_net **out);
+int aninerf_net_destroy(aninerf_net *net);
+
+/* One dense layer as the kernel consumes it (after the host-side folding described in DESIGN.md):
+ * W (n_out, k_in) row-major fp32, bias_table (n_tables, n_out) fp32 -- one bias row per latent
+ * index (the per-frame latent code is constant over a frame, so its contribution
+ * W[:, latent cols] @ latent is folded into the bias).  k_in is given WITHOUT padding.
+ * These are HOST pointers: loading is a once-per-checkpoint operation, the library packs the
+ * matrices into its tensor-core operand images on the host and uploads them. */
+typedef struct {
+  const float *W;
+  const float *bias_table;
+  int32_t n_out, k_in, n_tables, relu;
+} aninerf_layer;
+
+/* Upload one field.  Layer lists (k_in x n_out):
+ *  BW / NOVEL_BW (calculate_neural_blend_weights, tpose_nerf_network.py:55-77 / :304-315):
+ *     63x256, 4 x 256x256, (63+256)x256 [skip: PE first, then hidden], 2 x 256x256, 256x24
+ *  NERF (TPoseHuman.calculate_alpha_rgb, tpose_nerf_network.py:252-275):
+ *     63x256, 4 x 256x256, (63+256)x256, 2 x 256x256, (256+27)x128 [feature_fc o latent_fc o view_fc
+ *     folded], then heads passed separately: alpha_fc (1,256)+(1,), rgb_fc (3,128)+(3,).
+ * All pointers here are HOST fp32.  The call synchronises `stream` (it is not on the hot path). */
+int aninerf_net_load_field(aninerf_net *net, int32_t field, const aninerf_layer *layers_host, int32_t n_layers,
+                           const float *alpha_w_host, const float *alpha_b_host, const float *rgb_w_host,
+                           const float *rgb_b_host, void *stream);
+
+/* Blend-weight field forward (+ optional fused inverse LBS epilogue).
+ *  pts (n,3): query points (pose space for pbw / canonical space for tbw)
+ *  smpl_bw (n,24): initial SMPL weights (first 24 channels of aninerf_sample_blend_weights' rows,
+ *     repacked to 24-float rows); the fused render path samples them in-kernel instead
+ *  n_dev: optional device int32 holding the live row count (<= n) so the host never syncs
+ *  bw_out (n,24) or NULL; A (24,4,4) + tpts_out (n,3) or NULL: inverse-LBS epilogue
+ *     (Network.pose_points_to_tpose_points, tpose_nerf_network.py:79-100).
+ * precision: 3 = bf16x3 split products (fp32-equivalent, the 1e-5 gate), 1 = single bf16 pass. */
+int aninerf_bw_forward(aninerf_net *net, int32_t field, int32_t latent_index, const float *pts,
+                       const float *smpl_bw, int64_t n, const int32_t *n_dev, const float *A, float *bw_out,
+                       float *tpts_out, int32_t precision, void *stream);
+
+/* Canonical NeRF field forward: raw density + raw colour (pre-activation), optional fused tail of
+ * Network.forward (tpose_nerf_network.py:186-212): tbounds test, sigmoid, 1-exp(-relu(sigma)*dist),
+ * scatter to the dense raw buffer through `index`.
+ *  pts (n,3) canonical points; viewdir (n,3) world-space unit directions
+ *  sigma_out (n,), rgb_out (n,3): pre-activation outputs, may be NULL
+ *  tail: dists (n,), tbounds (2,3), index (n,) int32, raw_out (n_total,4) pre-zeroed; sigma_masked_out
+ *  (n,) optional (sigma after the tbounds masking, the `alpha` the reference thresholds at :192). */
+int aninerf_nerf_forward(aninerf_net *net, int32_t latent_index, const float *pts, const float *viewdir,
+                         int64_t n, const int32_t *n_dev, float *sigma_out, float *rgb_out,
+                         const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
+                         float *sigma_masked_out, int32_t precision, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The fused path: Renderer.render(batch), tpose_renderer.py:159-186 over
+ * Network.forward, tpose_nerf_network.py:139-215
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *A;        /* (24,4,4) */
+  const float *R;        /* (3,3) */
+  const float *Th;       /* (3,) */
+  const float *pbw;      /* (X,Y,Z,25) posed-space blend-weight volume */
+  const float *tbw;      /* (X',Y',Z',25) canonical volume */
+  const float *pbounds;  /* (2,3) */
+  const float *tbounds;  /* (2,3) */
+  int32_t pbw_dims[3];
+  int32_t tbw_dims[3];
+  int32_t latent_index;     /* batch['latent_index'] */
+  int32_t bw_latent_index;  /* batch['bw_latent_index'] (novel pose) */
+} aninerf_frame;
+
+typedef struct {
+  int32_t n_samples;      /* cfg.N_samples (<= 64, multiple of 32) */
+  int32_t chunk_rays;     /* 2048 */
+  float norm_th;          /* cfg.norm_th */
+  int32_t white_bkgd;     /* cfg.white_bkgd */
+  int32_t novel_pose;     /* cfg.test_novel_pose: use the NOVEL_BW field with bw_latent_index */
+  int32_t want_bw;        /* also evaluate the canonical tbw pass and emit pbw/tbw/sigma rows */
+  int32_t bw_precision;   /* 3 (default) or 1 */
+  int32_t nerf_precision; /* 1 (default) or 3 */
+} aninerf_render_params;
+
+typedef struct {
+  float *rgb_map;    /* (n_rays,3) */
+  float *acc_map;    /* (n_rays,) */
+  float *depth_map;  /* (n_rays,) */
+  float *raw;        /* (n_rays*S,4) dense; REQUIRED (also the compositing input) */
+  /* want_bw outputs, each with room for n_rays*S rows (only the first *n_active are written) */
+  float *pbw_all;      /* (n_active,24) */
+  float *tbw_all;      /* (n_active,24) */
+  float *sigma_masked; /* (n_active,) */
+  int32_t *active_index; /* (n_active,) flat sample index of each active row; may be NULL */
+  int32_t *n_active;   /* device int32: number of active samples (n'), REQUIRED */
+  int32_t *chunk_offsets; /* (n_chunks+1,) device int32: start row of every 2048-ray chunk in the
+                             compacted order; may be NULL */
+} aninerf_render_outputs;
+
+int64_t aninerf_render_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_t want_bw, int64_t pbw_voxels,
+                                       int64_t tbw_voxels);
+
+/* ray_o, ray_d (n_rays,3); near, far (n_rays,); t_vals (S,); t_rand (n_rays,S) or NULL. */
+int aninerf_render_rays(aninerf_net *net, const aninerf_frame *frame_host, const aninerf_render_params *params_host,
+                        const float *ray_o, const float *ray_d, const float *near, const float *far,
+                        const float *t_vals, const float *t_rand, int64_t n_rays,
+                        const aninerf_render_outputs *out_host, void *workspace, int64_t workspace_bytes,
+                        void *stream);
+
+/* Network.calculate_alpha (= get_alpha), tpose_nerf_network.py:105-137: density-only query of
+ * world points (norm_th hard-coded 0.1 by the reference -- passed in), processed in chunks of
+ * chunk_pts points (131072 in aninerf_mesh_renderer.py:35).  sigma_out (n,), zero where masked. */
+int aninerf_query_alpha(aninerf_net *net, const aninerf_frame *frame_host, const float *wpts, int64_t n,
+                        int64_t chunk_pts, float norm_th, int32_t novel_pose, int32_t bw_precision,
+                        float *sigma_out, int32_t *n_active, void *workspace, int64_t workspace_bytes,
+                        void *stream);
+int64_t aninerf_query_workspace_bytes(int64_t n, int64_t pbw_voxels);
+
+/* Counts launches of this library's kernels since process start (bench.py's gpu_launches). */
+int64_t aninerf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANINERF_B200_H */

@@ -1,0 +1,6 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference render hot path.
+
+Nothing in the product package (`animatable_nerf_b200/`) imports this package.
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import it, and only as the checker / CPU baseline.
+"""
