@@ -16,6 +16,8 @@ N_BONES = 24
 BW_CH = 25
 CHUNK_RAYS = 2048
 FIELD_BW, FIELD_NOVEL_BW, FIELD_NERF = 0, 1, 2
+STAGES = ('split_volumes', 'clear_raw', 'front_end', 'unused3', 'unused4', 'bw_field_posed', 'bw_field_canonical', 'nerf_field',
+          'composite')
 
 c_float_p = C.POINTER(C.c_float)
 c_i32_p = C.POINTER(C.c_int32)
@@ -54,6 +56,8 @@ PROTOTYPES = {
     'aninerf_version': (_I32, []),
     'aninerf_last_error': (C.c_char_p, []),
     'aninerf_launch_count': (_I64, []),
+    'aninerf_profile_enable': (_I32, [_I32]),
+    'aninerf_profile_read': (_I32, [C.POINTER(C.c_double), C.POINTER(C.c_int64), _I32]),
     'aninerf_gen_rays': (_I32, [C.POINTER(Camera), _VP, _VP, _VP]),
     'aninerf_near_far': (_I32, [c_float_p, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     'aninerf_compact_workspace_bytes': (_I64, [_I64]),

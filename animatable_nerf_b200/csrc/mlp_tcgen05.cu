@@ -84,7 +84,6 @@ struct MlpArgs {
   const int32_t *index;
   float *raw_out;
   float *sigma_masked_out;
-  int32_t desc_swap;       // debug: swap LBO/SBO roles
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -336,16 +335,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     // ===== MMA issuer ===========================================================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
-      const uint32_t a_lbo = args.desc_swap ? 128u : (uint32_t)CHUNK_BYTES;
-      const uint32_t a_sbo = args.desc_swap ? (uint32_t)CHUNK_BYTES : 128u;
+      const uint32_t a_lbo = (uint32_t)CHUNK_BYTES, a_sbo = 128u;   // K-direction / 8-row-group strides
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int s = 0; s < F.n_steps; ++s) {
           Step st = F.steps[s];
           const int n_pad = F.layers[st.layer].n_pad;
           const uint32_t idesc = instr_desc(n_pad);
           const uint32_t b_k_stride = (uint32_t)n_pad * 16u;       // bytes between K core matrices in the image
-          const uint32_t b_lbo = args.desc_swap ? 128u : b_k_stride;
-          const uint32_t b_sbo = args.desc_swap ? b_k_stride : 128u;
+          const uint32_t b_lbo = b_k_stride, b_sbo = 128u;
           if (st.flags & 1) {
             mbar_wait(bar_a_ready, a_phase);   // A operand of this layer written, accumulator drained
             a_phase ^= 1;
@@ -743,14 +740,7 @@ static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
   return ANINERF_OK;
 }
 
-static int desc_swap_flag() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("ANINERF_DESC_SWAP");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
-}
+
 
 static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs &a) {
   if (!net) return fail(ANINERF_EINVAL, "%s: null net%s", __func__);
@@ -766,7 +756,6 @@ static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs 
   memcpy(a.f.layers, f.layers, sizeof(f.layers));
   a.f.bias = f.bias;
   a.f.head = f.head;
-  a.desc_swap = desc_swap_flag();
   return ANINERF_OK;
 }
 

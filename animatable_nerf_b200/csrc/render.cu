@@ -1,6 +1,9 @@
 // The fused path behind Renderer.render(batch) (tpose_renderer.py:159-186 over Network.forward,
 // tpose_nerf_network.py:139-215) and the density query (Network.calculate_alpha, :105-137):
 // a stream-ordered chain of this library's kernels with every count kept on the device.
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace aninerf {
@@ -30,6 +33,44 @@ int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *
 int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
                       float *sigma_out, float *rgb_out, const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
                       float *sigma_masked_out, int precision, cudaStream_t st);
+
+// ---- optional per-stage timing (CUDA events on the launching stream) ---------------------------
+enum { ST_SPLIT = 0, ST_CLEAR, ST_MASK, ST_SCAN, ST_COMPACT, ST_BW_POSE, ST_BW_CANON, ST_NERF, ST_COMPOSITE, ST_COUNT };
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pending[ST_COUNT];
+static std::vector<cudaEvent_t> g_free_events;
+static double g_ms[ST_COUNT];
+static long long g_calls[ST_COUNT];
+
+static cudaEvent_t take_event() {
+  cudaEvent_t e;
+  if (!g_free_events.empty()) {
+    e = g_free_events.back();
+    g_free_events.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+
+struct StageTimer {   // records start on construction, stop on destruction
+  int stage;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(int stage_, cudaStream_t st_) : stage(stage_), st(st_) {
+    if (g_profile) {
+      a = take_event();
+      b = take_event();
+      cudaEventRecord(a, st);
+    }
+  }
+  ~StageTimer() {
+    if (a) {
+      cudaEventRecord(b, st);
+      g_pending[stage].push_back({a, b});
+    }
+  }
+};
 
 struct Carver {   // bump allocator over the caller's workspace (256-byte aligned pieces)
   char *base;
@@ -109,37 +150,84 @@ int aninerf_render_rays(aninerf_net *net, const aninerf_frame *fr, const aninerf
   const int64_t n = n_rays * S;
   int rc;
   // per-frame volume split (weights plane for the MLP head, distance plane for the mask pass)
-  if ((rc = launch_split_volume(fr->pbw, fr->pbw_dims, s.w24_p, s.dist_p, st))) return rc;
-  if (pr->want_bw && (rc = launch_split_volume(fr->tbw, fr->tbw_dims, s.w24_t, s.dist_t, st))) return rc;
-  ANI_CUDA(cudaMemsetAsync(out->raw, 0, n * 16, st));
+  {
+    StageTimer t(ST_SPLIT, st);
+    if ((rc = launch_split_volume(fr->pbw, fr->pbw_dims, s.w24_p, s.dist_p, st))) return rc;
+    if (pr->want_bw && (rc = launch_split_volume(fr->tbw, fr->tbw_dims, s.w24_t, s.dist_t, st))) return rc;
+  }
+  {
+    StageTimer t(ST_CLEAR, st);
+    ANI_CUDA(cudaMemsetAsync(out->raw, 0, n * 16, st));
+  }
   int32_t *index = out->active_index ? out->active_index : s.index;
   // 1. sample -> pose -> pnorm mask -> per-chunk argmin forcing -> stable compaction
-  if ((rc = launch_front_end(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, pr->chunk_rays, fr->R, fr->Th, fr->pbounds, fr->pbw_dims,
-                             s.dist_p, pr->norm_th, s.fb, index, s.ppts, s.viewdir, s.dists, out->n_active, out->chunk_offsets, st)))
-    return rc;
+  {
+    StageTimer t(ST_MASK, st);
+    if ((rc = launch_front_end(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, pr->chunk_rays, fr->R, fr->Th, fr->pbounds, fr->pbw_dims,
+                               s.dist_p, pr->norm_th, s.fb, index, s.ppts, s.viewdir, s.dists, out->n_active, out->chunk_offsets, st)))
+      return rc;
+  }
   // 2. neural blend weights at the posed points + inverse LBS -> canonical points
   const int bw_field = pr->novel_pose ? ANINERF_FIELD_NOVEL_BW : ANINERF_FIELD_BW;
   const int bw_latent = pr->novel_pose ? fr->bw_latent_index : fr->latent_index + 1;
   const int bw_prec = pr->bw_precision == 1 ? 1 : 3;
-  if ((rc = bw_forward_impl(net, bw_field, bw_latent, s.ppts, nullptr, s.w24_p, fr->pbw_dims, fr->pbounds, n, out->n_active, fr->A,
-                            pr->want_bw ? out->pbw_all : nullptr, s.tpts, bw_prec, st)))
-    return rc;
+  {
+    StageTimer t(ST_BW_POSE, st);
+    if ((rc = bw_forward_impl(net, bw_field, bw_latent, s.ppts, nullptr, s.w24_p, fr->pbw_dims, fr->pbounds, n, out->n_active, fr->A,
+                              pr->want_bw ? out->pbw_all : nullptr, s.tpts, bw_prec, st)))
+      return rc;
+  }
   // 3. (training contract only) blend weights of the canonical points, latent index 0
-  if (pr->want_bw &&
-      (rc = bw_forward_impl(net, ANINERF_FIELD_BW, 0, s.tpts, nullptr, s.w24_t, fr->tbw_dims, fr->tbounds, n, out->n_active, nullptr,
-                            out->tbw_all, nullptr, bw_prec, st)))
-    return rc;
+  if (pr->want_bw) {
+    StageTimer t(ST_BW_CANON, st);
+    if ((rc = bw_forward_impl(net, ANINERF_FIELD_BW, 0, s.tpts, nullptr, s.w24_t, fr->tbw_dims, fr->tbounds, n, out->n_active, nullptr,
+                              out->tbw_all, nullptr, bw_prec, st)))
+      return rc;
+  }
   // 4. canonical NeRF field + tail of Network.forward, scattered into the dense raw buffer
-  if ((rc = nerf_forward_impl(net, fr->latent_index, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds, index,
-                              out->raw, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st)))
-    return rc;
+  {
+    StageTimer t(ST_NERF, st);
+    if ((rc = nerf_forward_impl(net, fr->latent_index, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds, index,
+                                out->raw, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st)))
+      return rc;
+  }
   // 5. compositing
+  StageTimer t(ST_COMPOSITE, st);
   const float *z = nullptr;
   if (t_rand) {
     if ((rc = aninerf_sample_points(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, nullptr, s.z_vals, nullptr, stream))) return rc;
     z = s.z_vals;
   }
   return launch_composite_fused(out->raw, near, far, t_vals, z, n_rays, S, pr->white_bkgd, out->rgb_map, out->acc_map, out->depth_map, st);
+}
+
+int aninerf_profile_enable(int32_t on) {
+  g_profile = on != 0;
+  return ANINERF_OK;
+}
+
+int aninerf_profile_read(double *ms_out, int64_t *calls_out, int32_t reset) {
+  ANI_CHECK_ARG(ms_out && calls_out);
+  ANI_CUDA(cudaDeviceSynchronize());
+  for (int s = 0; s < ST_COUNT; ++s) {
+    for (auto &pr : g_pending[s]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        g_ms[s] += ms;
+        g_calls[s] += 1;
+      }
+      g_free_events.push_back(pr.first);
+      g_free_events.push_back(pr.second);
+    }
+    g_pending[s].clear();
+    ms_out[s] = g_ms[s];
+    calls_out[s] = g_calls[s];
+    if (reset) {
+      g_ms[s] = 0.0;
+      g_calls[s] = 0;
+    }
+  }
+  return ANINERF_OK;
 }
 
 int64_t aninerf_query_workspace_bytes(int64_t n, int64_t pbw_voxels) {

@@ -1,0 +1,63 @@
+"""Ray-tile sharding of one frame across the GPUs of a box (one process per GPU).
+
+Rays are independent; the only cross-ray coupling in the reference is the
+per-2048-ray-chunk argmin/argmax forcing (tpose_nerf_network.py:154, :193-194), so tiles are whole
+chunks of the reference's chunk grid, dealt round-robin to the ranks (load balance: neighbouring
+chunks cover neighbouring image rows).  Every rank then renders its tiles with the same kernels and
+the N-GPU image is bit-identical to the 1-GPU image.  The only collective is the final gather of the
+(rgb, acc, depth) tiles -- 20 B/ray -- over NCCL (gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+CHUNK = 2048
+PER_RAY_KEYS = ('ray_o', 'ray_d', 'near', 'far', 'occupancy', 'rgb', 'mask_at_box')
+
+
+def n_chunks(n_rays: int, chunk: int = CHUNK) -> int:
+    return (n_rays + chunk - 1) // chunk
+
+
+def chunks_of_rank(n_rays: int, rank: int, world: int, chunk: int = CHUNK):
+    return list(range(rank, n_chunks(n_rays, chunk), world))
+
+
+def shard_indices(n_rays: int, rank: int, world: int, chunk: int = CHUNK, device='cpu') -> torch.Tensor:
+    """Ray indices (ascending within each chunk, chunks in round-robin order) rendered by `rank`."""
+    parts = [torch.arange(c * chunk, min(n_rays, (c + 1) * chunk), device=device) for c in chunks_of_rank(n_rays, rank, world, chunk)]
+    return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.long, device=device)
+
+
+def shard_sizes(n_rays: int, world: int, chunk: int = CHUNK):
+    return [sum(min(n_rays, (c + 1) * chunk) - c * chunk for c in chunks_of_rank(n_rays, r, world, chunk)) for r in range(world)]
+
+
+def shard_batch(batch: dict, rank: int, world: int, chunk: int = CHUNK) -> dict:
+    """The rank's slice of a `Renderer.render` batch: per-ray keys are gathered, frame keys are shared."""
+    n_rays = batch['ray_o'].shape[1]
+    idx = shard_indices(n_rays, rank, world, chunk, device=batch['ray_o'].device)
+    out = dict(batch)
+    for k in PER_RAY_KEYS:
+        if k in batch and torch.is_tensor(batch[k]) and batch[k].dim() >= 2 and batch[k].shape[1] == n_rays:
+            out[k] = batch[k].index_select(1, idx)
+    return out
+
+
+def gather_maps(local: torch.Tensor, n_rays: int, rank: int, world: int, chunk: int = CHUNK, group=None) -> torch.Tensor:
+    """All-gather per-ray rows (R_local, C) from every rank and put them back in frame order -> (n_rays, C)."""
+    if world == 1:
+        return local
+    sizes = shard_sizes(n_rays, world, chunk)
+    pad = max(sizes)
+    C = local.shape[1]
+    send = torch.zeros(pad, C, dtype=local.dtype, device=local.device)
+    send[:local.shape[0]] = local
+    recv = torch.empty(world * pad, C, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    full = torch.empty(n_rays, C, dtype=local.dtype, device=local.device)
+    for r in range(world):
+        idx = shard_indices(n_rays, r, world, chunk, device=local.device)
+        full[idx] = recv[r * pad:r * pad + sizes[r]]
+    return full

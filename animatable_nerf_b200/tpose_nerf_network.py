@@ -194,7 +194,8 @@ class Network(nn.Module):
         v = _lib.f32c(vol)
         dims = (C.c_int32 * 3)(*v.shape[-4:-1])
         out = torch.empty(m, 25, device=p.device)
-        _lib.check(_lib.lib().aninerf_sample_blend_weights(_lib.ptr(p), m, _lib.ptr(v), dims, _lib.ptr(_lib.f32c(bounds)), _lib.ptr(out),
+        b = _lib.f32c(bounds)                                            # (locals keep every operand alive across the launch)
+        _lib.check(_lib.lib().aninerf_sample_blend_weights(_lib.ptr(p), m, _lib.ptr(v), dims, _lib.ptr(b), _lib.ptr(out),
                                                            _lib.stream_ptr()))
         return out.t().unsqueeze(0)
 
@@ -213,8 +214,9 @@ class Network(nn.Module):
     def _world_to_pose(self, wpts, batch):
         w = _points(wpts)
         out = torch.empty_like(w)
-        _lib.check(_lib.lib().aninerf_world_to_pose(_lib.ptr(w), w.shape[0], _lib.ptr(_lib.f32c(batch['R'])),
-                                                    _lib.ptr(_lib.f32c(batch['Th'])), _lib.ptr(out), _lib.stream_ptr()))
+        Rm, Th = _lib.f32c(batch['R']), _lib.f32c(batch['Th'])
+        _lib.check(_lib.lib().aninerf_world_to_pose(_lib.ptr(w), w.shape[0], _lib.ptr(Rm), _lib.ptr(Th), _lib.ptr(out),
+                                                    _lib.stream_ptr()))
         return out.unsqueeze(0)
 
     @torch.no_grad()

@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: samples/s and ms/frame of the aninerf_313 1024x1024 render.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one full frame through the hot path (`Renderer.render`: mask -> blend-weight MLP ->
+inverse LBS -> NeRF MLP -> compositing) for all rays that hit the SMPL box of a synthetic 1024x1024
+frame (BASELINE config 2).  `value` = nominal samples (rays x 64) of the frame / device time of the
+step with inputs resident in HBM; `e2e` = the same through `Renderer.render(batch)` from pinned host
+buffers with the host<->device copies inside the timed region.  N > 1 (torchrun): the frame's
+2048-ray chunks are dealt round-robin to the ranks and the image tiles are gathered over NCCL
+(strong scaling of one frame).  `--impl reference` times the reference algorithm's CPU port
+(oracle/) on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FLOP_BW = 2 * 562688        # algorithmic FLOP per active sample, blend-weight MLP
+FLOP_NERF = 2 * 691712      # canonical NeRF MLP (unfolded layer shapes)
+METRIC = 'samples/s (aninerf_313 1024x1024 frame render; ms/frame = ms_per_step)'
+WORKLOAD = 'aninerf_313 full 1024x1024 frame render (inverse LBS + canonical NeRF MLP + compositing), synthetic pose'
+CPU_SAMPLE_RAYS = 1024      # BASELINE config 1: 1024 rays x 64 samples on the CPU
+
+
+def peaks():
+    p = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ('hbm_gbs', 'bf16_tflops', 'bf16_tflops_sustained') if k in m})
+        p['source'] = 'measured'
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def build_workload(size):
+    """Synthetic aninerf_313 frame + camera (seeds: body 1, pose 2)."""
+    from animatable_nerf_b200 import synthetic
+    frame = synthetic.make_frame(pose_seed=2, body_seed=1, voxel=0.025, latent_index=0)
+    K, R, T = synthetic.make_camera(frame, size, size, focal=1070.0 * size / 1024.0)
+    sd = synthetic.make_state_dict(seed=0, num_train_frame=60)
+    return frame, (K, R, T), sd
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_render_rate(frame, cam, sd, size, reps, warm=1, n_rays=CPU_SAMPLE_RAYS):
+    from animatable_nerf_b200 import synthetic
+    from oracle import aninerf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    K, R, T = cam
+    ray_o, ray_d, near, far, _ = O.get_rays_within_bounds(size, size, K, R, T, frame['wbounds'])
+    # every k-th ray of the frame: the sample keeps the frame's mix of empty and body-crossing rays
+    sl = np.linspace(0, ray_o.shape[0] - 1, n_rays).astype(np.int64)
+    batch = synthetic.make_render_batch(frame, ray_o[sl], ray_d[sl], near[sl], far[sl])
+    cfg = O.OracleCfg(perturb=0.)
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        O.render(sd, batch, cfg)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    n = batch['ray_o'].shape[1] * 64
+    return n / float(np.median(times)), float(np.median(times)), n
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    frame, cam, sd = build_workload(args.size)
+    rate, sec, n = cpu_render_rate(frame, cam, sd, args.size, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    cores = os.cpu_count() or 1
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample': f'{CPU_SAMPLE_RAYS} rays (every k-th ray of the frame) x 64 samples per step (BASELINE config 1 size)'},
+        'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'oracle/ port of Renderer.render on {CPU_SAMPLE_RAYS} rays x 64 samples, torch {torch.__version__} CPU, '
+                                   f'{cores} threads, median of {max(1, args.steps)}'},
+        'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from animatable_nerf_b200 import _lib, config, frontend, ray_tiles, synthetic
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer import Renderer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+
+    frame, cam, sd = build_workload(args.size)
+    K, R, T = cam
+    ray_o, ray_d, near, far, mask = frontend.get_rays_within_bounds(args.size, args.size, K, R, T, frame['wbounds'], device=dev)
+    n_rays = ray_o.shape[0]
+    S = 64
+    cfg = config.make_cfg(perturb=0., b200_render_only=True)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    net.eval()
+    renderer = Renderer(net, cfg)
+
+    full = synthetic.make_render_batch(frame, ray_o, ray_d, near, far, device=dev)
+    mine = ray_tiles.shard_batch(full, rank, world)
+    my_rays = mine['ray_o'].shape[1]
+    host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in mine.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        out = renderer.render_device(mine, want_bw=False)
+        maps = torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1)
+        img = ray_tiles.gather_maps(maps, n_rays, rank, world)
+        return out, img
+
+    def step_e2e():
+        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        out = renderer.render_device(b, want_bw=False)
+        maps = torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1)
+        img = ray_tiles.gather_maps(maps, n_rays, rank, world)
+        return (img if rank == 0 else maps).to('cpu', non_blocking=False)
+
+    def timed(fn, steps, profile=False):
+        evs = []
+        L.aninerf_profile_enable(1 if profile else 0)
+        barrier()
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            evs.append((a, b))
+            del r
+        barrier()
+        L.aninerf_profile_enable(0)
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        out, _ = step_device()
+        step_e2e()
+    n_active = int(out['n_active'].item())
+    na = torch.tensor([n_active], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(na)
+    n_active_total = int(na.item())
+
+    import ctypes as C
+    ms_buf, calls_buf = (C.c_double * 9)(), (C.c_int64 * 9)()
+    L.aninerf_profile_read(ms_buf, calls_buf, 1)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.aninerf_launch_count()
+    total_ms = timed(lambda: step_device(), args.steps, profile=True)
+    launches = L.aninerf_launch_count() - launches0
+    L.aninerf_profile_read(ms_buf, calls_buf, 1)
+    stage_ms = {name: (ms_buf[i] / max(1, calls_buf[i])) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
+    e2e_ms = timed(lambda: step_e2e(), args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    samples = n_rays * S
+    ms_per_step = total_ms / args.steps
+    pk = peaks()
+    # dominant kernel = the slower of the two tcgen05 MLP launches of the frame (this rank's share)
+    cand = {'bw_field_posed': FLOP_BW, 'nerf_field': FLOP_NERF}
+    dom = max(cand, key=lambda k: stage_ms.get(k, 0.0))
+    dom_tflops = n_active * cand[dom] / (stage_ms[dom] * 1e-3) / 1e12
+    mlp_ms = stage_ms.get('bw_field_posed', 0.0) + stage_ms.get('nerf_field', 0.0)
+    roofline = {
+        'bound': 'tensor', 'kernel': 'mlp_kernel<3,false> (blend-weight field, bf16x3)' if dom == 'bw_field_posed' else 'mlp_kernel<1,true> (NeRF field, bf16)',
+        'achieved': dom_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': dom_tflops / pk['bf16_tflops_sustained'],
+        'traffic': None, 'peak_source': pk['source'] + ' (sustained bf16: kernel timed inside the step)',
+        'algorithmic_flop_per_active_sample': cand[dom], 'active_samples_per_launch': n_active, 'launch_ms': stage_ms[dom],
+        'both_mlps': {'tflops': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 if mlp_ms else None,
+                      'frac': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'] if mlp_ms else None},
+    }
+    line = {
+        'metric': METRIC, 'value': samples / (ms_per_step * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'rays_in_box': n_rays, 'n_samples': S, 'image': f'{args.size}x{args.size}',
+                   'active_samples': n_active_total, 'active_fraction': n_active_total / samples,
+                   'precision': 'blend-weight MLP bf16x3 split (fp32-equivalent), NeRF MLP bf16, fp32 accumulate',
+                   'mode': 'render-only (rgb/acc/depth; canonical tbw pass and raw/pbw/tbw outputs are training-contract outputs)',
+                   'l2': 'flushed between timed steps (256 MiB fill)', 'parallelism': f'ray tiles: 2048-ray chunks round-robin over {world} GPU(s)',
+                   'weights': 'random init, seed 0, reference checkpoint layout'},
+        'e2e': {'value': samples / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int((n_rays if rank == 0 else my_rays) * 20)},
+        'gpu_launches': int(launches),
+        'clocks': clk,
+        'roofline': roofline,
+        'stage_ms_rank0': stage_ms,
+        'active_samples_per_s': n_active_total / (ms_per_step * 1e-3),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, sec, n = cpu_render_rate(frame, cam, sd, args.size, reps=3)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                'sample': f'oracle/ port of Renderer.render, {CPU_SAMPLE_RAYS} rays x 64 samples of the same frame, '
+                                          f'torch {torch.__version__} CPU, median of 3 ({sec:.2f} s each)'}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--size', type=int, default=1024)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    return run_reference(args) if args.impl == 'reference' else run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

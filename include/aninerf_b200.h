@@ -233,6 +233,14 @@ int aninerf_query_alpha(aninerf_net *net, const aninerf_frame *frame_host, const
                         void *stream);
 int64_t aninerf_query_workspace_bytes(int64_t n, int64_t pbw_voxels);
 
+/* Optional per-stage device timing of aninerf_render_rays (CUDA events on the launching stream).
+ * Stage order: split volumes, clear raw, mask+scan+compact front end, (unused), (unused), blend-weight
+ * field at posed points (+LBS), blend-weight field at canonical points, NeRF field (+tail), compositing.
+ * aninerf_profile_read synchronises the device, returns accumulated milliseconds and call counts. */
+#define ANINERF_N_STAGES 9
+int aninerf_profile_enable(int32_t on);
+int aninerf_profile_read(double *ms_out_host, int64_t *calls_out_host, int32_t reset);
+
 /* Counts launches of this library's kernels since process start (bench.py's gpu_launches). */
 int64_t aninerf_launch_count(void);
 

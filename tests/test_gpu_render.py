@@ -1,0 +1,159 @@
+"""GPU parity of the fused path: Renderer.render(batch) through aninerf_render_rays vs the CPU oracle
+and vs the committed reference outputs (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, golden_small_case, load_golden, small_frame_case, to_device
+
+pytestmark = pytest.mark.gpu
+
+BW_TOL = 1e-5
+RGB_TOL = 2e-3
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'these tests need the B200'
+    return torch.device('cuda:0')
+
+
+def _renderer(dev, sd, **over):
+    from animatable_nerf_b200 import config
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer import Renderer
+    cfg = config.make_cfg(perturb=0., **over)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    return Renderer(net, cfg)
+
+
+def _check_maps(out, ref, tol=RGB_TOL):
+    for k in ('rgb_map', 'acc_map', 'depth_map'):
+        assert out[k].shape == ref[k].shape, k
+        assert float((out[k].cpu() - torch.as_tensor(ref[k])).abs().max()) <= tol, k
+
+
+def test_render_matches_reference_golden(dev):
+    """The committed REFERENCE outputs (2175 rays = one full 2048-ray chunk + a ragged one)."""
+    g, batch, sd = golden_small_case()
+    r = _renderer(dev, sd)
+    out = r.render(to_device(batch, dev))
+    assert set(out) == {'rgb_map', 'acc_map', 'depth_map', 'raw', 'pbw', 'tbw'}
+    assert all(not v.is_cuda for v in out.values())            # tpose_renderer.py:154-155
+    _check_maps(out, g)
+    assert out['raw'].shape == g['raw'].shape
+    assert float((out['raw'] - torch.from_numpy(g['raw'])).abs().max()) <= RGB_TOL
+    # the zero pattern of raw is the (bit-exact) pnorm mask
+    assert np.array_equal((out['raw'].numpy()[..., :3] != 0).any(-1), (g['raw'][..., :3] != 0).any(-1))
+
+
+def test_render_internals_vs_oracle(dev):
+    """Active set bit-exact; canonical points and both blend-weight fields within 1e-5; the pbw/tbw
+    row selection (alpha > train_th + per-chunk arg-max) reproduces the oracle's rows."""
+    _, _, batch, _ = small_frame_case(voxel=0.05, H=160, W=160, focal=170.0)
+    from animatable_nerf_b200 import synthetic
+    sd = synthetic.make_state_dict(seed=0)
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0.), return_debug=True)
+    dbg = ref['_debug']
+    r = _renderer(dev, sd)
+    dv = r.render_device(to_device(batch, dev), want_bw=True)
+    n_active = int(dv['n_active'].item())
+    pind = dbg['pind'].numpy()
+    assert n_active == int(pind.sum())
+    assert np.array_equal(dv['active_index'][:n_active].cpu().numpy(), np.nonzero(pind)[0].astype(np.int32))
+    assert np.array_equal(np.diff(dv['chunk_offsets'].cpu().numpy()), dbg['chunk_active'].numpy())
+    assert float((dv['pbw_all'][:n_active].cpu() - dbg['pbw_all']).abs().max()) <= BW_TOL
+    assert float((dv['tbw_all'][:n_active].cpu() - dbg['tbw_all']).abs().max()) <= 2 * BW_TOL   # canonical-point error feeds in
+    _check_maps({k: dv[k].view(ref[k].shape) for k in ('rgb_map', 'acc_map', 'depth_map')}, ref)
+    # `outside` (canonical tbounds test) sits behind the MLP: mismatches only for points within 1e-5 of a bound
+    sig = dv['sigma_masked'][:n_active].cpu()
+    out_gpu = sig == 0
+    mism = (out_gpu != dbg['outside']).nonzero().reshape(-1)
+    tb = batch['tbounds'][0]
+    for i in mism.tolist():
+        margin = torch.minimum((dbg['tpose'][i] - tb[0]).abs().min(), (dbg['tpose'][i] - tb[1]).abs().min())
+        assert float(margin) <= 1e-5, f'outside mismatch at row {i} with margin {float(margin)}'
+    # full contract through render()
+    out = r.render(to_device(batch, dev))
+    assert abs(out['pbw'].shape[1] - ref['pbw'].shape[1]) <= 4     # rows whose density sits within bf16 noise of train_th
+    if out['pbw'].shape == ref['pbw'].shape:
+        assert float((out['pbw'] - ref['pbw']).abs().max()) <= BW_TOL
+
+
+def test_render_with_jitter(dev):
+    g, batch, sd = golden_small_case()
+    r = _renderer(dev, sd)
+    t_rand = torch.from_numpy(g['jitter_t_rand'])
+    dv = r.render_device(to_device(batch, dev), t_rand=t_rand.to(dev), want_bw=False)
+    _check_maps({k: dv[k].view(g['jitter_' + k].shape) for k in ('rgb_map', 'acc_map', 'depth_map')},
+                {k: g['jitter_' + k] for k in ('rgb_map', 'acc_map', 'depth_map')})
+
+
+def test_render_novel_pose_field(dev):
+    from animatable_nerf_b200 import synthetic
+    g, batch, _ = golden_small_case()
+    g2 = load_golden('render_small_novel_pose.npz')
+    sd2 = synthetic.make_state_dict(seed=int(g2['sd_seed']), num_eval_frame=int(g2['num_eval_frame']))
+    r = _renderer(dev, sd2, aninerf_animation=True, test_novel_pose=True, num_eval_frame=int(g2['num_eval_frame']))
+    out = r.render(to_device(batch, dev))
+    _check_maps(out, g2)
+
+
+def test_render_only_mode_and_edge_sizes(dev):
+    g, batch, sd = golden_small_case()
+    r = _renderer(dev, sd, b200_render_only=True)
+    out = r.render(to_device(batch, dev))
+    assert set(out) == {'rgb_map', 'acc_map', 'depth_map'}
+    _check_maps(out, g)
+    for n in (1, 63, 2048, 2049):
+        sub = {k: (v[:, :n] if k in ('ray_o', 'ray_d', 'near', 'far', 'occupancy') else v) for k, v in batch.items()}
+        ref = O.render(sd, sub, O.OracleCfg(perturb=0.))
+        _check_maps(r.render(to_device(sub, dev)), ref)
+
+
+def test_chunk_with_no_active_sample_forces_argmin(dev):
+    """Rays that miss the SMPL shell entirely: the reference still evaluates one sample per chunk."""
+    _, batch, sd = golden_small_case()
+    sub = {k: (v[:, :300].clone() if k in ('ray_o', 'ray_d', 'near', 'far', 'occupancy') else v) for k, v in batch.items()}
+    sub['near'] = sub['near'] * 0 + 50.0
+    sub['far'] = sub['far'] * 0 + 51.0
+    ref = O.render(sd, sub, O.OracleCfg(perturb=0.), return_debug=True)
+    assert int(ref['_debug']['pind'].sum()) == 1
+    r = _renderer(dev, sd)
+    dv = r.render_device(to_device(sub, dev), want_bw=True)
+    assert int(dv['n_active'].item()) == 1
+    assert int(dv['active_index'][0].item()) == int(ref['_debug']['pind'].nonzero()[0, 0])
+    _check_maps({k: dv[k].view(ref[k].shape) for k in ('rgb_map', 'acc_map', 'depth_map')}, ref)
+
+
+def test_density_query(dev):
+    g, batch, sd = golden_small_case()
+    from animatable_nerf_b200 import config
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    net = Network(config.make_cfg())
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    pts, _ = O.sample_points(batch['ray_o'], batch['ray_d'], batch['near'], batch['far'], 64)
+    w = pts.view(-1, 3)[:20000]
+    got = net.get_alpha(w.to(dev), to_device(batch, dev))
+    ref = torch.from_numpy(g['alpha_grid'])
+    assert np.array_equal((got.cpu() != 0).numpy(), (ref != 0).numpy())      # mask (norm_th 0.1) bit-exact
+    assert float((got.cpu() - ref).abs().max()) <= 5e-3
+
+
+def test_network_forward_api(dev):
+    """Network.forward(wpts, viewdir, dists, batch) for one explicit chunk, as the reference renderer calls it."""
+    _, batch, sd = golden_small_case()
+    sub = {k: (v[:, :500] if k in ('ray_o', 'ray_d', 'near', 'far', 'occupancy') else v) for k, v in batch.items()}
+    pts, z = O.sample_points(sub['ray_o'], sub['ray_d'], sub['near'], sub['far'], 64)
+    wpts = pts.view(-1, 3)
+    vd = sub['ray_d'][0][:, None].repeat(1, 64, 1).view(-1, 3)
+    dists = O.sample_dists(z).view(-1)
+    ref = O.network_forward(sd, wpts, vd, dists, sub, O.OracleCfg())
+    r = _renderer(dev, sd)
+    out = r.net(wpts.to(dev), vd.to(dev), dists.to(dev), to_device(sub, dev))
+    assert out['raw'].shape == ref['raw'].shape
+    assert float((out['raw'].cpu() - ref['raw']).abs().max()) <= RGB_TOL
+    assert abs(out['pbw'].shape[1] - ref['pbw'].shape[1]) <= 2

@@ -1,0 +1,228 @@
+"""GPU parity, stage by stage, through the C ABI (libaninerf_b200.so) against the CPU oracle.
+
+Gates (BASELINE.json north_star): sampling / masking stages bit-exact; blend weights and canonical
+points <= 1e-5 abs (fp32); colour / density within 2e-3 where the bf16 MLP is used.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, golden_small_case, load_golden, small_frame_case, to_device
+
+pytestmark = pytest.mark.gpu
+
+BW_TOL = 1e-5      # blend weights, canonical points (north_star)
+RGB_TOL = 2e-3     # rgb / acc / depth with the bf16 MLP (north_star)
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'these tests need the B200'
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(scope='module')
+def L():
+    from animatable_nerf_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope='module')
+def case():
+    return small_frame_case(voxel=0.05, H=128, W=128, focal=130.0)
+
+
+def test_rays_and_box_bit_exact_vs_golden(dev):
+    from animatable_nerf_b200 import frontend
+    g = load_golden('stage1_rays_64.npz')
+    o, d = frontend.get_rays(64, 64, g['K'], g['R'], g['T'], device=dev)
+    assert np.array_equal(d.cpu().numpy(), g['rays_d'])
+    assert np.array_equal(o.cpu().numpy(), g['rays_o'])
+    ray_o, ray_d, near, far, mask = frontend.get_rays_within_bounds(64, 64, g['K'], g['R'], g['T'], g['bounds'], device=dev)
+    assert np.array_equal(mask.cpu().numpy(), g['mask_at_box'])
+    for a, b in ((ray_o, g['ray_o']), (ray_d, g['ray_d']), (near, g['near']), (far, g['far'])):
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_rays_and_box_bit_exact_full_frame(dev):
+    """BASELINE config 2 size: 1024x1024, all 1 048 576 rays, bit-exact mask / near / far / directions."""
+    from animatable_nerf_b200 import frontend, synthetic
+    frame = synthetic.make_frame(voxel=0.1)
+    K, R, T = synthetic.make_camera(frame, 1024, 1024)
+    ref = O.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'])
+    got = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    assert np.array_equal(got[4].cpu().numpy(), ref[4])
+    for a, b in zip(got[:4], ref[:4]):
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_empty_box_and_single_pixel(dev):
+    from animatable_nerf_b200 import frontend, synthetic
+    frame = synthetic.make_frame(voxel=0.1)
+    K, R, T = synthetic.make_camera(frame, 8, 8, focal=8.0)
+    far_bounds = frame['wbounds'] + 100.0          # box nowhere near the frustum
+    o, d, near, far, mask = frontend.get_rays_within_bounds(8, 8, K, R, T, far_bounds, device=dev)
+    assert o.shape == (0, 3) and near.numel() == 0 and not mask.any()
+    o1, d1 = frontend.get_rays(1, 1, K, R, T, device=dev)
+    ro, rd = O.get_rays(1, 1, K, R, T)
+    assert np.array_equal(d1.cpu().numpy(), rd.astype(np.float32))
+
+
+@pytest.mark.parametrize('jitter', [False, True])
+def test_sample_points_bit_exact(dev, L, case, jitter):
+    _, _, batch, _ = case
+    R_ = batch['ray_o'].shape[1]
+    t_rand = torch.rand(1, R_, 64, generator=torch.Generator().manual_seed(5)) if jitter else None
+    pts, z = O.sample_points(batch['ray_o'], batch['ray_d'], batch['near'], batch['far'], 64, t_rand)
+    dists = O.sample_dists(z)
+    b = to_device(batch, dev)
+    tv = torch.linspace(0., 1., 64).to(dev)
+    gp = torch.empty(R_ * 64, 3, device=dev)
+    gz = torch.empty(R_, 64, device=dev)
+    gd = torch.empty(R_ * 64, device=dev)
+    tr = t_rand.to(dev).contiguous() if jitter else None
+    ins = [b[k][0].contiguous() for k in ('ray_o', 'ray_d', 'near', 'far')]
+    L.check(L.lib().aninerf_sample_points(L.ptr(ins[0]), L.ptr(ins[1]), L.ptr(ins[2]), L.ptr(ins[3]), L.ptr(tv), L.ptr(tr), R_, 64,
+                                          L.ptr(gp), L.ptr(gz), L.ptr(gd), L.stream_ptr()))
+    assert np.array_equal(gz.cpu().numpy(), z[0].numpy())
+    assert np.array_equal(gp.cpu().numpy(), pts[0].reshape(-1, 3).numpy())
+    assert np.array_equal(gd.cpu().numpy(), dists[0].reshape(-1).numpy())
+
+
+def _pose_points(batch, n=None):
+    pts, _ = O.sample_points(batch['ray_o'], batch['ray_d'], batch['near'], batch['far'], 64)
+    w = pts.view(1, -1, 3)
+    if n:
+        w = w[:, :n]
+    return w, O.world_to_pose(w, batch['R'], batch['Th'])
+
+
+def test_world_to_pose_and_volume_sampling_bit_exact(dev, case):
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200 import config
+    _, _, batch, _ = case
+    w, pp = _pose_points(batch)
+    init = O.sample_blend_weights(pp, batch['pbw'], batch['pbounds'])
+    net = Network(config.make_cfg())
+    b = to_device(batch, dev)
+    gpp = net._world_to_pose(w.to(dev), b)
+    assert np.array_equal(gpp.cpu().numpy(), pp.numpy())
+    ginit = net._sample_volume(gpp, b['pbw'], b['pbounds'])
+    # the distance channel decides the mask: bit-exact; so are the 24 weight channels
+    assert np.array_equal(ginit.cpu().numpy(), init.numpy())
+    # out-of-volume points exercise the border clamp
+    far_pts = (torch.rand(1, 5000, 3, generator=torch.Generator().manual_seed(1)) - 0.5) * 6
+    assert np.array_equal(net._sample_volume(far_pts.to(dev), b['pbw'], b['pbounds']).cpu().numpy(),
+                          O.sample_blend_weights(far_pts, batch['pbw'], batch['pbounds']).numpy())
+
+
+def test_lbs_forward_inverse(dev, L, case):
+    _, _, batch, _ = case
+    _, pp = _pose_points(batch, 30000)
+    g = torch.Generator().manual_seed(3)
+    bw = torch.softmax(torch.randn(1, 24, pp.shape[1], generator=g) * 2, dim=1)
+    tp = O.inverse_lbs(pp, bw, batch['A'])
+    fw = O.forward_lbs(tp, bw, batch['A'])
+    n = pp.shape[1]
+    bwd = bw[0].t().contiguous().to(dev)
+    A = batch['A'][0].contiguous().to(dev)
+    gt = torch.empty(n, 3, device=dev)
+    gf = torch.empty(n, 3, device=dev)
+    ppd = pp[0].contiguous().to(dev)
+    L.check(L.lib().aninerf_inverse_lbs(L.ptr(ppd), L.ptr(bwd), n, L.ptr(A), L.ptr(gt), L.stream_ptr()))
+    L.check(L.lib().aninerf_forward_lbs(L.ptr(gt), L.ptr(bwd), n, L.ptr(A), L.ptr(gf), L.stream_ptr()))
+    assert (gt.cpu() - tp[0]).abs().max() <= BW_TOL
+    assert (gf.cpu() - fw[0]).abs().max() <= BW_TOL
+    # round trip: forward(inverse(x)) == x
+    assert (gf.cpu() - pp[0]).abs().max() <= BW_TOL
+
+
+def test_composite(dev, L):
+    g = torch.Generator().manual_seed(7)
+    for R_ in (1, 31, 2048 + 77):
+        raw = torch.rand(R_, 64, 4, generator=g)
+        raw[..., 3] = raw[..., 3] ** 3
+        raw[R_ // 2, 10:, 3] = 1.0          # fully opaque sample: the 1e-10 floor path
+        raw[0, :, 3] = 0.0                  # empty ray
+        z = torch.sort(torch.rand(R_, 64, generator=g) * 2 + 2, dim=1)[0]
+        rgb, disp, acc, w, depth = O.raw2outputs(raw, z, False)
+        out = [torch.empty(R_, 3, device=dev), torch.empty(R_, device=dev), torch.empty(R_, device=dev), torch.empty(R_, device=dev),
+               torch.empty(R_, 64, device=dev)]
+        raw_d, z_d = raw.to(dev), z.to(dev)      # keep the device copies alive across the launch
+        L.check(L.lib().aninerf_composite(L.ptr(raw_d), L.ptr(z_d), R_, 64, 0, L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]),
+                                          L.ptr(out[3]), L.ptr(out[4]), L.stream_ptr()))
+        assert (out[0].cpu() - rgb).abs().max() <= 1e-5
+        assert (out[1].cpu() - acc).abs().max() <= 1e-5
+        assert (out[2].cpu() - depth).abs().max() <= 2e-5
+        assert (out[4].cpu() - w).abs().max() <= 1e-6
+        # white background variant
+        L.check(L.lib().aninerf_composite(L.ptr(raw_d), L.ptr(z_d), R_, 64, 1, L.ptr(out[0]), None, None, None, None,
+                                          L.stream_ptr()))
+        assert (out[0].cpu() - O.raw2outputs(raw, z, True)[0]).abs().max() <= 1e-5
+
+
+def _net(dev, sd, **cfg_over):
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200 import config
+    net = Network(config.make_cfg(**cfg_over))
+    net.load_state_dict(sd)
+    return net.to(dev)
+
+
+def test_blend_weight_field_1e5(dev, case):
+    """bf16x3 tcgen05 MLP + softmax + fused inverse LBS: weights and canonical points within 1e-5."""
+    from animatable_nerf_b200 import synthetic
+    _, _, batch, _ = case
+    sd = synthetic.make_state_dict(seed=0)
+    _, pp = _pose_points(batch, 20000 + 37)                       # ragged last tile
+    init = O.sample_blend_weights(pp, batch['pbw'], batch['pbounds'])[:, :24]
+    idx = batch['latent_index'] + 1
+    bw = O.neural_blend_weights(sd, pp, init, idx)
+    tp = O.inverse_lbs(pp, bw, batch['A'])
+    net = _net(dev, sd)
+    b = to_device(batch, dev)
+    gbw = net.calculate_neural_blend_weights(pp.to(dev), init.to(dev), idx.to(dev))
+    assert gbw.shape == bw.shape
+    assert (gbw.cpu() - bw).abs().max() <= BW_TOL
+    gtp, gpbw = net.pose_points_to_tpose_points(pp.to(dev), b)
+    assert (gpbw.cpu() - bw).abs().max() <= BW_TOL
+    assert (gtp.cpu() - tp).abs().max() <= BW_TOL
+
+
+def test_blend_weight_field_sharper_weights(dev, case):
+    """'trained-like' sharper field (all layer weights x1.6): bf16x3 must still hold 1e-5."""
+    from animatable_nerf_b200 import synthetic
+    _, _, batch, _ = case
+    sd = synthetic.make_state_dict(seed=2, gain=1.6)
+    _, pp = _pose_points(batch, 8192)
+    init = O.sample_blend_weights(pp, batch['pbw'], batch['pbounds'])[:, :24]
+    idx = batch['latent_index'] + 1
+    bw = O.neural_blend_weights(sd, pp, init, idx)
+    net = _net(dev, sd)
+    gbw = net.calculate_neural_blend_weights(pp.to(dev), init.to(dev), idx.to(dev))
+    assert (gbw.cpu() - bw).abs().max() <= BW_TOL
+
+
+def test_nerf_field(dev, case):
+    from animatable_nerf_b200 import synthetic
+    _, _, batch, _ = case
+    sd = synthetic.make_state_dict(seed=0)
+    g = torch.Generator().manual_seed(11)
+    n = 10000 + 3
+    lo, hi = batch['tbounds'][0, 0], batch['tbounds'][0, 1]
+    pts = (torch.rand(1, n, 3, generator=g) * (hi - lo) + lo)
+    vd = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=2)
+    alpha, rgb = O.nerf_alpha_rgb(sd, pts, vd, batch['latent_index'])
+    net = _net(dev, sd)
+    ga, gr = net.tpose_human.calculate_alpha_rgb(pts.to(dev), vd.to(dev), batch['latent_index'].to(dev))
+    assert ga.shape == alpha.shape and gr.shape == rgb.shape
+    # single-pass bf16: pre-activation density / colour logits, 2e-3 after the activations downstream
+    assert (ga.cpu() - alpha).abs().max() <= 5e-3
+    assert (torch.sigmoid(gr.cpu()) - torch.sigmoid(rgb)).abs().max() <= RGB_TOL
+    # the split-precision instantiation of the same kernel is fp32-equivalent
+    net3 = _net(dev, sd, b200_nerf_precision=3)
+    ga3, gr3 = net3.tpose_human.calculate_alpha_rgb(pts.to(dev), vd.to(dev), batch['latent_index'].to(dev))
+    assert (ga3.cpu() - alpha).abs().max() <= 2e-5
+    assert (gr3.cpu() - rgb).abs().max() <= 2e-5

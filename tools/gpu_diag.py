@@ -1,0 +1,125 @@
+"""Bring-up diagnostics for a GPU box: runs each stage against the oracle and prints the numbers
+(never asserts), so that one gpurun call yields the full picture.  Output: gpurun_out/diag.log"""
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from helpers import O, golden_small_case, small_frame_case, to_device  # noqa: E402
+from animatable_nerf_b200 import _lib, config, synthetic  # noqa: E402
+from animatable_nerf_b200.tpose_nerf_network import Network  # noqa: E402
+from animatable_nerf_b200.tpose_renderer import Renderer  # noqa: E402
+
+dev = torch.device('cuda:0')
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+LOG = open(os.path.join(ROOT, 'gpurun_out', 'diag.log'), 'a')
+
+
+def say(*a):
+    msg = ' '.join(str(x) for x in a)
+    print(msg, flush=True)
+    LOG.write(msg + '\n')
+    LOG.flush()
+
+
+def md(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+def section(name, fn):
+    say(f'--- {name}')
+    try:
+        fn()
+    except Exception:
+        say('EXCEPTION', traceback.format_exc())
+
+
+def mlp_checks():
+    _, _, batch, _ = small_frame_case(voxel=0.05, H=128, W=128, focal=130.0)
+    sd = synthetic.make_state_dict(seed=0)
+    g = torch.Generator().manual_seed(11)
+    n = 4096 + 5
+    lo, hi = batch['tbounds'][0, 0], batch['tbounds'][0, 1]
+    pts = torch.rand(1, n, 3, generator=g) * (hi - lo) + lo
+    vd = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=2)
+    alpha, rgb = O.nerf_alpha_rgb(sd, pts, vd, batch['latent_index'])
+    init = O.sample_blend_weights(pts, batch['tbw'], batch['tbounds'])[:, :24]
+    bw = O.neural_blend_weights(sd, pts, init, batch['latent_index'] + 1)
+    for swap in (0,):
+        for prec in (1, 3):
+            try:
+                net = Network(config.make_cfg(b200_nerf_precision=prec, b200_bw_precision=prec))
+                net.load_state_dict(sd)
+                net = net.to(dev)
+                ga, gr = net.tpose_human.calculate_alpha_rgb(pts.to(dev), vd.to(dev), batch['latent_index'].to(dev))
+                torch.cuda.synchronize()
+                say(f'swap={swap} prec={prec} NERF: alpha maxdiff {md(ga, alpha):.3e} (|alpha| max {float(alpha.abs().max()):.3f}) '
+                    f'rgb maxdiff {md(gr, rgb):.3e}')
+                gb = net.calculate_neural_blend_weights(pts.to(dev), init.to(dev), (batch['latent_index'] + 1).to(dev))
+                torch.cuda.synchronize()
+                say(f'swap={swap} prec={prec} BW  : bw maxdiff {md(gb, bw):.3e}')
+            except Exception:
+                say(f'swap={swap} prec={prec} EXCEPTION', traceback.format_exc())
+                return
+
+
+def render_check():
+    g, batch, sd = golden_small_case()
+    cfg = config.make_cfg(perturb=0.)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    r = Renderer(net, cfg)
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0.), return_debug=True)
+    dv = r.render_device(to_device(batch, dev), want_bw=True)
+    torch.cuda.synchronize()
+    na = int(dv['n_active'].item())
+    say('n_active gpu', na, 'oracle', int(ref['_debug']['pind'].sum()), 'of', ref['_debug']['pind'].numel())
+    if na == int(ref['_debug']['pind'].sum()):
+        say('active index equal:', bool(np.array_equal(dv['active_index'][:na].cpu().numpy(), np.nonzero(ref['_debug']['pind'].numpy())[0])))
+        say('pbw_all maxdiff', md(dv['pbw_all'][:na], ref['_debug']['pbw_all']), 'tbw_all', md(dv['tbw_all'][:na], ref['_debug']['tbw_all']))
+    for k in ('rgb_map', 'acc_map', 'depth_map', 'raw'):
+        say(k, 'maxdiff vs oracle', md(dv[k].view(ref[k].shape), ref[k]), 'vs golden', md(dv[k].view(ref[k].shape), torch.from_numpy(g[k])))
+
+
+def timing():
+    frame = synthetic.make_frame(voxel=0.025)
+    K, R, T = synthetic.make_camera(frame, 1024, 1024)
+    from animatable_nerf_b200 import frontend
+    ray_o, ray_d, near, far, mask = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    say('rays in box', ray_o.shape[0])
+    batch = synthetic.make_render_batch(frame, ray_o, ray_d, near, far, device=dev)
+    sd = synthetic.make_state_dict(seed=0)
+    for render_only in (True, False):
+        cfg = config.make_cfg(perturb=0., b200_render_only=render_only)
+        net = Network(cfg)
+        net.load_state_dict(sd)
+        net = net.to(dev)
+        r = Renderer(net, cfg)
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dv = r.render_device(batch, want_bw=not render_only)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            na = int(dv['n_active'].item())
+            say(f'render_only={render_only} iter {it}: {dt * 1e3:.2f} ms, n_active {na} ({na / (ray_o.shape[0] * 64):.3f}), '
+                f'{ray_o.shape[0] * 64 / dt / 1e6:.1f} Msamples/s')
+
+
+if __name__ == '__main__':
+    say('=== gpu_diag', time.strftime('%H:%M:%S'), torch.cuda.get_device_name(0))
+    which = sys.argv[1:] or ['mlp', 'render', 'timing']
+    if 'mlp' in which:
+        section('mlp', mlp_checks)
+    if 'render' in which:
+        section('render', render_check)
+    if 'timing' in which:
+        section('timing', timing)
