@@ -56,6 +56,7 @@ PROTOTYPES = {
     'aninerf_version': (_I32, []),
     'aninerf_last_error': (C.c_char_p, []),
     'aninerf_launch_count': (_I64, []),
+    'aninerf_debug_set_trace': (_I32, [_VP]),
     'aninerf_profile_enable': (_I32, [_I32]),
     'aninerf_profile_read': (_I32, [C.POINTER(C.c_double), C.POINTER(C.c_int64), _I32]),
     'aninerf_gen_rays': (_I32, [C.POINTER(Camera), _VP, _VP, _VP]),

@@ -84,7 +84,15 @@ struct MlpArgs {
   const int32_t *index;
   float *raw_out;
   float *sigma_masked_out;
+  unsigned long long *trace;   // bring-up: clock64 timeline of block 0's first tile (null = off)
 };
+
+// trace slots: 0 tile start, 1 PE done; per layer l (base 8 + 8*l): +0 rows wait begin, +1 rows woke,
+// +2 rows epilogue done (arrived); +4 MMA waits a_ready, +5 MMA woke, +6 MMA issued all steps of the layer
+#define ANI_TRACE(slot)                                                              \
+  do {                                                                               \
+    if (tracing) args.trace[(slot)] = (unsigned long long)clock64();                 \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       uint32_t stage = 0, phase = 0, a_phase = 0;
       const uint32_t a_lbo = (uint32_t)CHUNK_BYTES, a_sbo = 128u;   // K-direction / 8-row-group strides
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const bool tracing = args.trace && blockIdx.x == 0 && tile == 0;
         for (int s = 0; s < F.n_steps; ++s) {
           Step st = F.steps[s];
           const int n_pad = F.layers[st.layer].n_pad;
@@ -344,8 +353,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           const uint32_t b_k_stride = (uint32_t)n_pad * 16u;       // bytes between K core matrices in the image
           const uint32_t b_lbo = b_k_stride, b_sbo = 128u;
           if (st.flags & 1) {
+            ANI_TRACE(8 + 8 * st.layer + 4);
             mbar_wait(bar_a_ready, a_phase);   // A operand of this layer written, accumulator drained
             a_phase ^= 1;
+            ANI_TRACE(8 + 8 * st.layer + 5);
           }
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -365,7 +376,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             }
           }
           umma_commit(bar_empty + 8 * stage);        // frees the ring stage once these MMAs retire
-          if (st.flags & 2) umma_commit(bar_acc);    // layer done: accumulator ready for the epilogue
+          if (st.flags & 2) {
+            umma_commit(bar_acc);                    // layer done: accumulator ready for the epilogue
+            ANI_TRACE(8 + 8 * st.layer + 6);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -381,6 +395,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t gi = tile * TILE_M + row;
       const bool valid = gi < n_valid;
+      const bool tracing = args.trace && blockIdx.x == 0 && tile == 0 && row == 0;
+      ANI_TRACE(0);
       float px = 0.f, py = 0.f, pz = 0.f;
       if (valid) {
         px = __ldg(args.pts + 3 * gi);
@@ -399,6 +415,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       }
       fence_proxy_async();
       mbar_arrive(bar_a_ready);
+      ANI_TRACE(1);
 
       float sigma = 0.f;   // NeRF: alpha_fc evaluated in fp32 inside the layer-7 epilogue
       for (int l = 0; l < F.n_layers; ++l) {
@@ -447,9 +464,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             }
           }
         }
+        ANI_TRACE(8 + 8 * l);
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        ANI_TRACE(8 + 8 * l + 1);
         const float *bias = s_bias + l * 256;
         const int n_pad = F.layers[l].n_pad;
         if (!last) {
@@ -485,6 +504,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(bar_a_ready);
+          ANI_TRACE(8 + 8 * l + 2);
         } else if (!NERF) {
           // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
           uint32_t v[32];
@@ -742,6 +762,8 @@ static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
 
 
 
+static unsigned long long *g_trace = nullptr;
+
 static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs &a) {
   if (!net) return fail(ANINERF_EINVAL, "%s: null net%s", __func__);
   if (field < 0 || field >= ANINERF_N_FIELDS) return fail(ANINERF_EINVAL, "%s: bad field%s", __func__);
@@ -756,6 +778,7 @@ static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs 
   memcpy(a.f.layers, f.layers, sizeof(f.layers));
   a.f.bias = f.bias;
   a.f.head = f.head;
+  a.trace = g_trace;
   return ANINERF_OK;
 }
 
@@ -810,6 +833,11 @@ int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, cons
 using namespace aninerf;
 
 extern "C" {
+
+int aninerf_debug_set_trace(unsigned long long *device_buf) {
+  g_trace = device_buf;
+  return ANINERF_OK;
+}
 
 int aninerf_net_create(aninerf_net **out) {
   ANI_CHECK_ARG(out);

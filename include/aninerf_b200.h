@@ -241,6 +241,10 @@ int64_t aninerf_query_workspace_bytes(int64_t n, int64_t pbw_voxels);
 int aninerf_profile_enable(int32_t on);
 int aninerf_profile_read(double *ms_out_host, int64_t *calls_out_host, int32_t reset);
 
+/* Bring-up aid: when set to a device buffer of >= 128 uint64, the MLP kernels write a clock64
+ * timeline of block 0's first tile into it (slot map in csrc/mlp_tcgen05.cu).  NULL disables. */
+int aninerf_debug_set_trace(unsigned long long *device_buf);
+
 /* Counts launches of this library's kernels since process start (bench.py's gpu_launches). */
 int64_t aninerf_launch_count(void);
 

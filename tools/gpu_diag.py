@@ -123,3 +123,39 @@ if __name__ == '__main__':
         section('render', render_check)
     if 'timing' in which:
         section('timing', timing)
+
+
+def trace():
+    """clock64 timeline of one tile of each MLP kernel (block 0, first tile)."""
+    _, _, batch, _ = small_frame_case(voxel=0.05, H=128, W=128, focal=130.0)
+    sd = synthetic.make_state_dict(seed=0)
+    n = 148 * 128 * 4
+    g = torch.Generator().manual_seed(11)
+    lo, hi = batch['tbounds'][0, 0], batch['tbounds'][0, 1]
+    pts = (torch.rand(1, n, 3, generator=g) * (hi - lo) + lo).to(dev)
+    vd = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=2).to(dev)
+    init = torch.softmax(torch.randn(1, 24, n, generator=g), dim=1).to(dev)
+    net = Network(config.make_cfg())
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    buf = torch.zeros(256, dtype=torch.int64, device=dev)
+    for name, fn in (('NERF x1', lambda: net.tpose_human.calculate_alpha_rgb(pts, vd, batch['latent_index'].to(dev))),
+                     ('BW x3', lambda: net.calculate_neural_blend_weights(pts, init, (batch['latent_index'] + 1).to(dev)))):
+        fn()
+        torch.cuda.synchronize()
+        buf.zero_()
+        _lib.lib().aninerf_debug_set_trace(buf.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        _lib.lib().aninerf_debug_set_trace(None)
+        t = buf.cpu().numpy()
+        t0 = t[0]
+        say(f'{name}: tile start 0, PE done {t[1] - t0}')
+        for l in range(9):
+            b = 8 + 8 * l
+            say(f'  L{l}: mma wait_a {t[b + 4] - t0} woke {t[b + 5] - t0} issued {t[b + 6] - t0} | rows wait {t[b] - t0} woke {t[b + 1] - t0} '
+                f'done {t[b + 2] - t0 if t[b + 2] else 0}  || mma phase {t[b + 1] - t[b + 5]} (issue {t[b + 6] - t[b + 5]}) epilogue {t[b + 2] - t[b + 1] if t[b + 2] else 0}')
+
+
+if 'trace' in sys.argv[1:]:
+    section('trace', trace)
