@@ -2,20 +2,28 @@
 // :304-315) and the canonical NeRF MLP (tpose_nerf_network.py:252-275) -- as ONE persistent,
 // warp-specialised tcgen05 kernel family for sm_100a.
 //
-// Per CTA (one per SM): a 128-sample tile lives in shared memory as the bf16 A operand of every
-// layer (K-major, no-swizzle core-matrix layout [K/8][128 rows][8]); weights stream from L2 through
-// a ring of 16 KB stages filled by bulk TMA copies (cp.async.bulk) of pre-packed operand images;
-// one elected thread issues tcgen05.mma (M=128, N<=256, K=16) into a 256-column fp32 TMEM
-// accumulator; four epilogue warps (thread == row == TMEM lane) read it back with tcgen05.ld,
-// apply bias+ReLU, re-quantise to bf16 (hi, and lo for the split-precision mode) and write the next
-// layer's A operand in place.  Positional encoding is generated in-kernel straight into the A
-// operand; the last epilogue is the field's head (softmax + inverse LBS, or alpha/rgb activation +
-// tbounds masking + scatter).
+// Work unit: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2).  Each CTA owns 128 samples per tile
+// slot: their bf16 A operand lives in its shared memory (K-major, no-swizzle core-matrix layout
+// [K/8][128 rows][8]) and their fp32 accumulator in its TMEM (128 lanes x 256 columns per slot).
+// Weights stream from L2 through a ring of 16 KB stages filled by bulk TMA copies (cp.async.bulk)
+// of pre-packed operand images; each CTA of the pair loads HALF of every chunk (the M=256 MMA reads
+// B from both CTAs), which halves the L2 -> SM weight traffic per sample.  One elected thread of the
+// leader CTA issues tcgen05.mma (M=256, N<=256, K=16); eight epilogue warps per CTA (two threads per
+// row, each owning half of the columns) read the accumulator back with tcgen05.ld, apply bias+ReLU,
+// re-quantise to bf16 (hi, and lo for the split-precision mode) and write the next layer's A operand
+// in place.  Positional encoding is generated in-kernel straight into the A operand; the last
+// epilogue is the field's head (softmax + inverse LBS, or alpha/rgb activation + tbounds masking +
+// scatter).
+//
+// NT = 2 (single-pass precision): each CTA holds TWO tile slots and ping-pongs them -- while the
+// tensor core runs layer l of slot 1 the epilogue warps drain layer l of slot 0 -- so MMA and epilogue
+// overlap.  NT = 1 for the split-precision mode (its A operand, hi+lo, fills shared memory).
 //
 // Precision modes: NPASS=1 single bf16 product; NPASS=3 "bf16x3": x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // with fp32 accumulation (fp32-equivalent; the blend-weight field needs it for the 1e-5 gate).
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -27,17 +35,20 @@ namespace aninerf {
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_M = 128;
 constexpr int CHUNK_BYTES = TILE_M * 16;     // one 8-wide K chunk of the A tile: 128 rows x 16 B
-constexpr int PE_CHUNK0 = 0;                 // A chunks 0..7   : PE(xyz) 63 + pad
-constexpr int HID_CHUNK0 = 8;                // A chunks 8..39  : hidden 256
-constexpr int VIEW_CHUNK0 = 40;              // A chunks 40..43 : PE(viewdir) 27 + pad (NeRF only)
+constexpr int PE_CHUNK0 = 0;                 // A chunks 0..7  : PE(xyz) 63 + pad; reused for PE(viewdir) once layer 5 has run
+constexpr int HID_CHUNK0 = 8;                // A chunks 8..39 : hidden 256
+constexpr int A_CHUNKS = 40;
+constexpr int A_BYTES = A_CHUNKS * CHUNK_BYTES;   // 80 KB per tile slot (per hi / lo plane)
 constexpr int STAGE_BYTES = 16384;
 constexpr int MAX_LAYERS = 9;
+constexpr int MAX_STEPS = 128;
 constexpr int BIAS_FLOATS = MAX_LAYERS * 256;
 constexpr int SMEM_LIMIT = 232448;           // 227 KB
+constexpr int VIEW_LAYER_WRITE = 6;          // PE(viewdir) is written during this layer's epilogue (layer 5 was the last PE(xyz) reader)
 
 struct Step {          // one weight-ring stage worth of MMAs
-  uint32_t w_off;      // byte offset of this step's operand image (hi, then lo) in the packed buffer
-  uint32_t bytes;      // bytes to copy (hi [+ lo])
+  uint32_t w_off;      // byte offset of this step's operand image in the packed buffer: [CTA0: hi, lo][CTA1: hi, lo]
+  uint32_t bytes;      // bytes of the whole step (all CTAs of the pair)
   uint16_t a_chunk;    // first A chunk consumed
   uint16_t n_k16;      // K=16 MMAs (per pass) in this step
   uint16_t layer;
@@ -45,11 +56,13 @@ struct Step {          // one weight-ring stage worth of MMAs
 };
 
 struct LayerDev {
-  int32_t n_pad;       // MMA N (multiple of 16)
+  int32_t n_pad;       // MMA N (multiple of 32)
   int32_t n_out;       // real outputs
   int32_t relu;
   int32_t bias_off;    // float offset of this layer's bias table inside `bias`
   int32_t n_tables;
+  int32_t step0;       // first step of the layer
+  int32_t n_steps;
 };
 
 struct FieldDev {
@@ -84,11 +97,11 @@ struct MlpArgs {
   const int32_t *index;
   float *raw_out;
   float *sigma_masked_out;
-  unsigned long long *trace;   // bring-up: clock64 timeline of block 0's first tile (null = off)
+  unsigned long long *trace;   // bring-up: clock64 timeline of block 0's first unit tile (null = off)
 };
 
-// trace slots: 0 tile start, 1 PE done; per layer l (base 8 + 8*l): +0 rows wait begin, +1 rows woke,
-// +2 rows epilogue done (arrived); +4 MMA waits a_ready, +5 MMA woke, +6 MMA issued all steps of the layer
+// trace slots: 0 tile start, 1 PE done; per (layer l, slot t) base 8 + 16*l + 8*t: +0 rows wait begin,
+// +1 rows woke, +2 rows epilogue done (arrived); +4 MMA waits a_ready, +5 MMA woke, +6 MMA issued the layer
 #define ANI_TRACE(slot)                                                              \
   do {                                                                               \
     if (tracing) args.trace[(slot)] = (unsigned long long)clock64();                 \
@@ -105,27 +118,43 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+  if (CLUSTER) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
 // bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+template <bool CLUSTER = false>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0) {
+  if (mbar_try_wait<CLUSTER>(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("aninerf mlp: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  while (!mbar_try_wait<CLUSTER>(bar, parity)) {
+    if (clock64() - t0 > 2000000000ll) {
+      printf("aninerf mlp: mbarrier timeout at wait site %d (block %d thread %d bar %u parity %u)\n", site, blockIdx.x, threadIdx.x, bar,
+             parity);
       __trap();
     }
   }
@@ -141,24 +170,71 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                : "memory");
 }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+// one lane of the (converged) warp: lets the surrounding loop stay warp-uniform so that descriptors live in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+template <int PAIR>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if (PAIR == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+}
+template <int PAIR>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  if (PAIR == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+template <int PAIR>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (PAIR == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive on the barrier at this shared-memory offset in EVERY CTA of the pair once the MMAs issued so far retire
+template <int PAIR>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (PAIR == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  }
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -180,117 +256,153 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
-__device__ __forceinline__ uint32_t instr_desc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// instruction descriptor: D=f32, A=B=bf16, both K-major
+__device__ __forceinline__ uint32_t instr_desc(int n, int m) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&v);
 }
-__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+// (relu(a), relu(b)) packed as bf16: the ReLU rides on the conversion instruction
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// residuals of a packed bf16 pair: (a - bf16(a), b - bf16(b)) packed as bf16
+__device__ __forceinline__ uint32_t pack_bf16_residual(float a, float b, uint32_t hi) {
+  float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  return pack_bf16(a - ha, b - hb);
+}
 
-// write 8 consecutive K elements of `row` (one 16-byte core-matrix row) into A chunk `chunk`
-template <int NPASS>
+// write 8 consecutive K elements of `row` (one 16-byte core-matrix row) into A chunk `chunk`;
+// RELU (single-pass mode only): x holds pre-activation values, the ReLU is applied by the conversion
+template <int NPASS, bool RELU = false>
 __device__ __forceinline__ void store_chunk(uint8_t *a_hi, uint8_t *a_lo, int chunk, int row, const float (&x)[8]) {
+  static_assert(!(RELU && NPASS == 3), "the split-precision residual needs the activated fp32 value");
   uint4 h;
-  h.x = pack_bf16(x[0], x[1]);
-  h.y = pack_bf16(x[2], x[3]);
-  h.z = pack_bf16(x[4], x[5]);
-  h.w = pack_bf16(x[6], x[7]);
+  if (RELU) {
+    h.x = pack_bf16_relu(x[0], x[1]);
+    h.y = pack_bf16_relu(x[2], x[3]);
+    h.z = pack_bf16_relu(x[4], x[5]);
+    h.w = pack_bf16_relu(x[6], x[7]);
+  } else {
+    h.x = pack_bf16(x[0], x[1]);
+    h.y = pack_bf16(x[2], x[3]);
+    h.z = pack_bf16(x[4], x[5]);
+    h.w = pack_bf16(x[6], x[7]);
+  }
   *reinterpret_cast<uint4 *>(a_hi + chunk * CHUNK_BYTES + row * 16) = h;
   if (NPASS == 3) {
-    float r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = x[j] - bf16_round(x[j]);
     uint4 l;
-    l.x = pack_bf16(r[0], r[1]);
-    l.y = pack_bf16(r[2], r[3]);
-    l.z = pack_bf16(r[4], r[5]);
-    l.w = pack_bf16(r[6], r[7]);
+    l.x = pack_bf16_residual(x[0], x[1], h.x);
+    l.y = pack_bf16_residual(x[2], x[3], h.y);
+    l.z = pack_bf16_residual(x[4], x[5], h.z);
+    l.w = pack_bf16_residual(x[6], x[7], h.w);
     *reinterpret_cast<uint4 *>(a_lo + chunk * CHUNK_BYTES + row * 16) = l;
   }
 }
 
-// NeRF positional encoding of a 3-vector (embedder.py:11-36): [x, sin(2^0 x), cos(2^0 x), ...], 3-wide blocks
-template <int NPASS, int L>
+// NeRF positional encoding of a 3-vector (embedder.py:11-36): [x, sin(2^0 x), cos(2^0 x), ...] in 3-wide
+// blocks; writes the 8-wide K chunks [CB, CE) of the encoding into A chunks chunk0+CB ... (each of the
+// two threads that share a row takes half of the chunks)
+template <int NPASS, int L, int CB, int CE>
 __device__ __forceinline__ void write_pe(uint8_t *a_hi, uint8_t *a_lo, int chunk0, int row, float px, float py, float pz) {
-  constexpr int NV = 3 + 6 * L;                 // 63 or 27
-  constexpr int NCH = (NV + 7) / 8;             // 8 or 4
-  float v[NCH * 8];
-  v[0] = px;
-  v[1] = py;
-  v[2] = pz;
-  float p[3] = {px, py, pz};
+  constexpr int NV = 3 + 6 * L;                                   // 63 or 27
+  constexpr int J0 = CB * 8, J1 = CE * 8;                         // value range [J0, J1)
+  constexpr int F0 = J0 <= 3 ? 0 : (J0 - 3) / 6;
+  constexpr int F1 = ((J1 < NV ? J1 : NV) - 1 - 3) / 6;           // last frequency touched
+  const float p[3] = {px, py, pz};
+  float sn[F1 - F0 + 1][3], cs[F1 - F0 + 1][3];
 #pragma unroll
-  for (int f = 0; f < L; ++f) {
-    float fr = (float)(1 << f);
+  for (int f = F0; f <= F1; ++f) {
+    const float fr = (float)(1 << f);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float s, co;
-      sincosf(p[c] * fr, &s, &co);
-      v[3 + 6 * f + c] = s;
-      v[3 + 6 * f + 3 + c] = co;
-    }
+    for (int c = 0; c < 3; ++c) sincosf(p[c] * fr, &sn[f - F0][c], &cs[f - F0][c]);
   }
 #pragma unroll
-  for (int j = NV; j < NCH * 8; ++j) v[j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
+  for (int ch = CB; ch < CE; ++ch) {
     float x[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = v[c * 8 + j];
-    store_chunk<NPASS>(a_hi, a_lo, chunk0 + c, row, x);
+    for (int j = 0; j < 8; ++j) {
+      const int v = ch * 8 + j;
+      if (v < 3) x[j] = p[v];
+      else if (v >= NV) x[j] = 0.f;
+      else {
+        const int f = (v - 3) / 6, r = (v - 3) % 6;
+        x[j] = r < 3 ? sn[f - F0][r] : cs[f - F0][r - 3];
+      }
+    }
+    store_chunk<NPASS>(a_hi, a_lo, chunk0 + ch, row, x);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NPASS, bool NERF>
+constexpr int ROW_WARPS = 8;                       // two threads per row: each takes half of the columns
+constexpr int ROW_THREADS = ROW_WARPS * 32;        // 256
+constexpr int N_THREADS = ROW_THREADS + 96;        // + warp 8: weight producer, warps 9-10: MMA issue (one thread per tile slot) / TMEM alloc / relay
+constexpr int XCHG_BYTES = TILE_M * 4 * 4;         // per-row exchange between the two column halves
+constexpr int PROD_LANES = 8;                      // producer lanes take turns issuing the bulk copies: one thread keeps only
+                                                   // ~one copy in flight (20-28 B/cycle, tools/bench_stream.cu); several
+                                                   // threads overlap theirs (4 threads: 85-110 B/cycle)
+
+template <int NPASS, bool NERF, int NT>
 struct Cfg {
-  static constexpr int A_CHUNKS = NERF ? 44 : 40;
-  static constexpr int A_BYTES = A_CHUNKS * CHUNK_BYTES;
-  static constexpr int A_TOTAL = A_BYTES * (NPASS == 3 ? 2 : 1);
+  static constexpr int A_TOTAL = A_BYTES * NT * (NPASS == 3 ? 2 : 1);
   static constexpr int HEAD_BYTES = NERF ? 2576 : 1152;
-  static constexpr int FIXED = A_TOTAL + BIAS_FLOATS * 4 + HEAD_BYTES + 256;
+  static constexpr int STEP_BYTES = MAX_STEPS * (int)sizeof(Step);
+  static constexpr int FIXED = A_TOTAL + BIAS_FLOATS * 4 + HEAD_BYTES + XCHG_BYTES * NT + STEP_BYTES + 256;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM = FIXED + STAGES * STAGE_BYTES;
   static_assert(STAGES >= 2, "weight ring needs at least two stages");
+  static constexpr int TMEM_COLS = 256 * NT;
   // offsets
-  static constexpr int OFF_A_HI = 0;
-  static constexpr int OFF_A_LO = A_BYTES;                      // only when NPASS == 3
+  static constexpr int OFF_A_HI = 0;                            // slot t at t * A_BYTES
+  static constexpr int OFF_A_LO = A_BYTES * NT;                 // only when NPASS == 3
   static constexpr int OFF_RING = A_TOTAL;
   static constexpr int OFF_BIAS = OFF_RING + STAGES * STAGE_BYTES;
   static constexpr int OFF_HEAD = OFF_BIAS + BIAS_FLOATS * 4;
-  static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
+  static constexpr int OFF_XCHG = OFF_HEAD + HEAD_BYTES;
+  static constexpr int OFF_STEPS = OFF_XCHG + XCHG_BYTES * NT;
+  static constexpr int OFF_BAR = OFF_STEPS + STEP_BYTES;
 };
 
-constexpr int N_THREADS = 192;   // warps 0-3: rows / epilogue; warp 4: weight producer; warp 5: TMEM alloc + MMA issue
-
-template <int NPASS, bool NERF>
+template <int NPASS, bool NERF, int PAIR, int NT>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant__ MlpArgs args) {
-  using C = Cfg<NPASS, NERF>;
+  using C = Cfg<NPASS, NERF, NT>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *a_hi = smem + C::OFF_A_HI;
-  uint8_t *a_lo = smem + C::OFF_A_LO;
   uint8_t *ring = smem + C::OFF_RING;
   float *s_bias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
   float *s_head = reinterpret_cast<float *>(smem + C::OFF_HEAD);
+  float *s_xchg = reinterpret_cast<float *>(smem + C::OFF_XCHG);
+  Step *s_steps = reinterpret_cast<Step *>(smem + C::OFF_STEPS);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-  // barrier slots: [0..S) full, [S..2S) empty, 2S: a_ready, 2S+1: acc_ready
+  // barrier slots: [0,S) full, [S,2S) empty, [2S,2S+NT) a_ready (leader), [2S+NT,2S+2NT) acc
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
   const uint32_t bar_a_ready = smem_u32(bars + 2 * C::STAGES);
-  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + 1);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2);
+  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + NT);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2 * NT);
+  static_assert((2 * C::STAGES + 2 * NT + 1) * 8 <= 192, "barrier block overflow");
+  // last weight-stream position consumed from each ring stage: with one MMA thread per slot a thread only waits
+  // on the `full` phases of its OWN steps, and a parity wait is only sound once the previous phase is known complete
+  volatile uint32_t *s_last = reinterpret_cast<volatile uint32_t *>(smem + C::OFF_BAR + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int n_units = (int)gridDim.x / PAIR;            // clusters walking the unit-tile list
+  const int unit = (int)blockIdx.x / PAIR;
   const FieldDev &F = args.f;
   const int64_t n_valid = args.n_dev ? (int64_t)min((int64_t)*args.n_dev, args.n) : args.n;
   const int64_t n_tiles = (n_valid + TILE_M - 1) / TILE_M;
+  constexpr int UT = PAIR * NT;                         // 128-row tiles per unit tile
+  const int64_t n_utiles = (n_tiles + UT - 1) / UT;
 
   // ---- one-time setup --------------------------------------------------------------------
   for (int i = threadIdx.x; i < BIAS_FLOATS; i += N_THREADS) {
@@ -302,6 +414,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     }
     s_bias[i] = b;
   }
+  for (int i = threadIdx.x; i < F.n_steps; i += N_THREADS) s_steps[i] = F.steps[i];
   if (NERF) {
     for (int i = threadIdx.x; i < 644; i += N_THREADS) s_head[i] = F.head[i];
   } else if (args.A) {
@@ -309,77 +422,121 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, (leader && PAIR == 2) ? 2 : 1);   // own bytes landed (+ the peer's relay on the leader)
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_a_ready, TILE_M);
-    mbar_init(bar_acc, 1);
+    for (int t = 0; t < NT; ++t) {
+      mbar_init(bar_a_ready + 8 * t, ROW_THREADS * PAIR);
+      mbar_init(bar_acc + 8 * t, 1);
+    }
+    for (int s = 0; s < C::STAGES; ++s) s_last[s] = 0xffffffffu;
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 9) tmem_alloc<PAIR>(smem_u32(tmem_slot), C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (PAIR == 2) cluster_sync_all();        // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ===== weight producer: stream the packed operand images through the ring =================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int s = 0; s < F.n_steps; ++s) {
-          Step st = F.steps[s];
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          mbar_expect_tx(bar_full + 8 * stage, st.bytes);
-          bulk_g2s(smem_u32(ring + stage * STAGE_BYTES), F.image + st.w_off, st.bytes, bar_full + 8 * stage);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
+  if (warp == 8) {
+    // ===== weight producer: this CTA's half of every operand image chunk ======================
+    if (lane < PROD_LANES) {
+      uint32_t stage = 0, phase = 0, turn = 0;
+      for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+        for (int l = 0; l < F.n_layers; ++l) {
+          for (int t = 0; t < NT; ++t) {
+            for (int s = F.layers[l].step0; s < F.layers[l].step0 + F.layers[l].n_steps; ++s) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);               // all producer lanes stay in step (no divergent spin)
+              if (turn == (uint32_t)lane) {
+                const uint32_t bytes = s_steps[s].bytes / PAIR;             // this CTA's half of the chunk
+                mbar_expect_tx(bar_full + 8 * stage, bytes);
+                bulk_g2s(smem_u32(ring + stage * STAGE_BYTES), F.image + s_steps[s].w_off + cta_rank * bytes, bytes, bar_full + 8 * stage);
+              }
+              __syncwarp((1u << PROD_LANES) - 1u);
+              turn = (turn + 1) % PROD_LANES;
+              if (++stage == C::STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
           }
         }
       }
     }
-  } else if (warp == 5) {
-    // ===== MMA issuer ===========================================================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
+  } else if (warp >= 9) {
+    const int my_slot = warp - 9;
+    if (leader && my_slot < NT) {
+      // ===== MMA issuers (leader CTA): one thread per tile slot, so that neither slot's issue stream
+      // waits behind the other's epilogue and the per-step barrier/commit overhead is split in two ====
+      uint32_t g = 0, a_phase = 0;                                  // g: position in the shared weight stream
       const uint32_t a_lbo = (uint32_t)CHUNK_BYTES, a_sbo = 128u;   // K-direction / 8-row-group strides
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const bool tracing = args.trace && blockIdx.x == 0 && tile == 0;
-        for (int s = 0; s < F.n_steps; ++s) {
-          Step st = F.steps[s];
-          const int n_pad = F.layers[st.layer].n_pad;
-          const uint32_t idesc = instr_desc(n_pad);
-          const uint32_t b_k_stride = (uint32_t)n_pad * 16u;       // bytes between K core matrices in the image
+      const int t = my_slot;
+      const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI + t * A_BYTES), a_lo = smem_u32(smem + C::OFF_A_LO + t * A_BYTES);
+      const uint32_t acc = tmem_base + (uint32_t)(t * 256);
+      for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+        const bool tracing = args.trace && blockIdx.x == 0 && ut == 0 && lane == 0;
+        for (int l = 0; l < F.n_layers; ++l) {
+          const int n_pad = F.layers[l].n_pad;
+          const int s0 = F.layers[l].step0, n_layer_steps = F.layers[l].n_steps;
+          const uint32_t idesc = instr_desc(n_pad, TILE_M * PAIR);
+          const uint32_t b_k_stride = (uint32_t)(n_pad / PAIR) * 16u;   // bytes between K core matrices (this CTA's rows)
           const uint32_t b_lbo = b_k_stride, b_sbo = 128u;
-          if (st.flags & 1) {
-            ANI_TRACE(8 + 8 * st.layer + 4);
-            mbar_wait(bar_a_ready, a_phase);   // A operand of this layer written, accumulator drained
-            a_phase ^= 1;
-            ANI_TRACE(8 + 8 * st.layer + 5);
-          }
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t b_hi = smem_u32(ring + stage * STAGE_BYTES);
-          const uint32_t b_lo = b_hi + (uint32_t)st.n_k16 * 2u * b_k_stride;
-          for (int k = 0; k < st.n_k16; ++k) {
-            const uint32_t a_off = (uint32_t)(st.a_chunk + 2 * k) * CHUNK_BYTES;
-            const uint64_t adh = smem_desc(smem_u32(a_hi) + a_off, a_lbo, a_sbo);
-            const uint64_t bdh = smem_desc(b_hi + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
-            const uint32_t fresh = ((st.flags & 1) && k == 0) ? 0u : 1u;
-            umma_bf16(tmem_base, adh, bdh, idesc, fresh);
-            if (NPASS == 3) {
-              const uint64_t adl = smem_desc(smem_u32(a_lo) + a_off, a_lbo, a_sbo);
-              const uint64_t bdl = smem_desc(b_lo + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
-              umma_bf16(tmem_base, adl, bdh, idesc, 1u);
-              umma_bf16(tmem_base, adh, bdl, idesc, 1u);
+          g += (uint32_t)(t * n_layer_steps);                           // the earlier slots' copies of this layer
+          ANI_TRACE(8 + 16 * l + 8 * t + 4);
+          mbar_wait<PAIR == 2>(bar_a_ready + 8 * t, a_phase, 2 + 10 * t);   // every row of the slot wrote its A operand, accumulator drained
+          a_phase ^= 1;
+          ANI_TRACE(8 + 16 * l + 8 * t + 5);
+          for (int s = s0; s < s0 + n_layer_steps; ++s, ++g) {
+            const Step st = s_steps[s];
+            const uint32_t stage = g % C::STAGES, phase = (g / C::STAGES) & 1u;
+            if (NT > 1 && g >= (uint32_t)C::STAGES) {
+              // the previous use of this stage (possibly the other slot's) must have been consumed first
+              long long t0 = clock64();
+              while (s_last[stage] != g - C::STAGES) {
+                if (clock64() - t0 > 2000000000ll) {
+                  printf("aninerf mlp: ring order timeout (block %d slot %d g %u)\n", blockIdx.x, t, g);
+                  __trap();
+                }
+              }
             }
+            mbar_wait(bar_full + 8 * stage, phase, 3 + 10 * t);   // TMA-written operands: CTA-scope acquire is enough for the async proxy
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(ring + stage * STAGE_BYTES);
+            const uint32_t b_lo = b_hi + (uint32_t)st.n_k16 * 2u * b_k_stride;
+            if (elect_one()) {
+              for (int k = 0; k < st.n_k16; ++k) {
+                const uint32_t a_off = (uint32_t)(st.a_chunk + 2 * k) * CHUNK_BYTES;
+                const uint64_t adh = smem_desc(a_hi + a_off, a_lbo, a_sbo);
+                const uint64_t bdh = smem_desc(b_hi + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
+                const uint32_t fresh = (s == s0 && k == 0) ? 0u : 1u;
+                umma_bf16<PAIR>(acc, adh, bdh, idesc, fresh);
+                if (NPASS == 3) {
+                  const uint64_t adl = smem_desc(a_lo + a_off, a_lbo, a_sbo);
+                  const uint64_t bdl = smem_desc(b_lo + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
+                  umma_bf16<PAIR>(acc, adl, bdh, idesc, 1u);
+                  umma_bf16<PAIR>(acc, adh, bdl, idesc, 1u);
+                }
+              }
+              if (NT > 1) s_last[stage] = g;
+              umma_commit<PAIR>(bar_empty + 8 * stage);        // frees the ring stage (both CTAs) once these MMAs retire
+              if (s == s0 + n_layer_steps - 1) umma_commit<PAIR>(bar_acc + 8 * t);   // layer done for this slot: accumulators ready
+            }
+            __syncwarp();
           }
-          umma_commit(bar_empty + 8 * stage);        // frees the ring stage once these MMAs retire
-          if (st.flags & 2) {
-            umma_commit(bar_acc);                    // layer done: accumulator ready for the epilogue
-            ANI_TRACE(8 + 8 * st.layer + 6);
-          }
+          ANI_TRACE(8 + 16 * l + 8 * t + 6);
+          g += (uint32_t)((NT - 1 - t) * n_layer_steps);      // the later slots' copies of this layer
+        }
+      }
+    } else if (lane == 0 && PAIR == 2 && !leader && my_slot == 0) {
+      // ===== relay (peer CTA): tell the leader when this CTA's half of a stage has landed ========
+      uint32_t stage = 0, phase = 0;
+      const uint32_t full_leader = mapa_u32(bar_full, 0);
+      const int64_t total = (int64_t)F.n_steps * NT;
+      for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+        for (int64_t s = 0; s < total; ++s) {
+          mbar_wait(bar_full + 8 * stage, phase, 4);
+          mbar_arrive_cluster(full_leader + 8 * stage);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -389,205 +546,252 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     }
   } else {
     // ===== row threads: input encoding, per-layer epilogues, heads =============================
-    const int row = threadIdx.x;                       // == TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int row = (warp & 3) * 32 + lane;            // == TMEM lane; warps w and w+4 share a row
+    const int half = warp >> 2;                        // which half of the columns this thread owns
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t a_ready_leader = PAIR == 2 ? mapa_u32(bar_a_ready, 0) : bar_a_ready;
     uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t gi = tile * TILE_M + row;
-      const bool valid = gi < n_valid;
-      const bool tracing = args.trace && blockIdx.x == 0 && tile == 0 && row == 0;
+    for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+      const bool tracing = args.trace && blockIdx.x == 0 && ut == 0 && threadIdx.x == 0;
+      int64_t gi[NT];
+      bool valid[NT];
+      float px[NT], py[NT], pz[NT], sigma[NT];
       ANI_TRACE(0);
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (valid) {
-        px = __ldg(args.pts + 3 * gi);
-        py = __ldg(args.pts + 3 * gi + 1);
-        pz = __ldg(args.pts + 3 * gi + 2);
-      }
-      write_pe<NPASS, 10>(a_hi, a_lo, PE_CHUNK0, row, px, py, pz);
-      if (NERF) {
-        float vx = 0.f, vy = 0.f, vz = 0.f;
-        if (valid) {
-          vx = __ldg(args.viewdir + 3 * gi);
-          vy = __ldg(args.viewdir + 3 * gi + 1);
-          vz = __ldg(args.viewdir + 3 * gi + 2);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
+        gi[t] = ((ut * NT + t) * PAIR + cta_rank) * TILE_M + row;
+        valid[t] = gi[t] < n_valid;
+        px[t] = py[t] = pz[t] = 0.f;
+        sigma[t] = 0.f;
+        if (valid[t]) {
+          px[t] = __ldg(args.pts + 3 * gi[t]);
+          py[t] = __ldg(args.pts + 3 * gi[t] + 1);
+          pz[t] = __ldg(args.pts + 3 * gi[t] + 2);
         }
-        write_pe<NPASS, 4>(a_hi, a_lo, VIEW_CHUNK0, row, vx, vy, vz);
+        if (half == 0) write_pe<NPASS, 10, 0, 4>(a_hi, a_lo, PE_CHUNK0, row, px[t], py[t], pz[t]);
+        else write_pe<NPASS, 10, 4, 8>(a_hi, a_lo, PE_CHUNK0, row, px[t], py[t], pz[t]);
+        fence_proxy_async();
+        if (leader) mbar_arrive(bar_a_ready + 8 * t);
+        else mbar_arrive_cluster(a_ready_leader + 8 * t);
       }
-      fence_proxy_async();
-      mbar_arrive(bar_a_ready);
       ANI_TRACE(1);
 
-      float sigma = 0.f;   // NeRF: alpha_fc evaluated in fp32 inside the layer-7 epilogue
       for (int l = 0; l < F.n_layers; ++l) {
         const bool last = l == F.n_layers - 1;
-        float smpl[ANINERF_N_BONES];
-        if (!NERF && last) {
-          // initial SMPL weights of this row, fetched while the last layer's MMAs run
+        const float *bias = s_bias + l * 256;
+        const int n_pad = F.layers[l].n_pad;
 #pragma unroll
-          for (int k = 0; k < ANINERF_N_BONES; ++k) smpl[k] = 0.f;
-          if (valid) {
-            if (args.smpl_bw) {
-              const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi * ANINERF_N_BONES);
+        for (int t = 0; t < NT; ++t) {
+          uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
+          float *xchg = s_xchg + t * (TILE_M * 4);           // this slot's exchange between the row's two threads
+          const uint32_t t_acc = t_lane + (uint32_t)(t * 256);
+          float smpl[ANINERF_N_BONES];
+          if (!NERF && last && half == 0) {
+            // initial SMPL weights of this row, fetched while the last layer's MMAs run
 #pragma unroll
-              for (int q = 0; q < 6; ++q) {
-                float4 t = __ldg(r4 + q);
-                smpl[4 * q] = t.x;
-                smpl[4 * q + 1] = t.y;
-                smpl[4 * q + 2] = t.z;
-                smpl[4 * q + 3] = t.w;
-              }
-            } else {
-              float w[8];
-              int off[8];
-              VolumeGrid vg;
+            for (int k = 0; k < ANINERF_N_BONES; ++k) smpl[k] = 0.f;
+            if (valid[t]) {
+              if (args.smpl_bw) {
+                const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi[t] * ANINERF_N_BONES);
 #pragma unroll
-              for (int a3 = 0; a3 < 3; ++a3) {
-                vg.lo[a3] = __ldg(args.grid_bounds + a3);
-                vg.ext[a3] = __fsub_rn(__ldg(args.grid_bounds + 3 + a3), vg.lo[a3]);
-                vg.dim[a3] = args.grid_dim[a3];
-              }
-              trilinear_corners(vg, px, py, pz, w, off);
+                for (int q = 0; q < 6; ++q) {
+                  float4 w4 = __ldg(r4 + q);
+                  smpl[4 * q] = w4.x;
+                  smpl[4 * q + 1] = w4.y;
+                  smpl[4 * q + 2] = w4.z;
+                  smpl[4 * q + 3] = w4.w;
+                }
+              } else {
+                float w[8];
+                int off[8];
+                VolumeGrid vg;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                if (off[c] >= 0) {
-                  const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)off[c] * ANINERF_N_BONES);
+                for (int a3 = 0; a3 < 3; ++a3) {
+                  vg.lo[a3] = __ldg(args.grid_bounds + a3);
+                  vg.ext[a3] = __fsub_rn(__ldg(args.grid_bounds + 3 + a3), vg.lo[a3]);
+                  vg.dim[a3] = args.grid_dim[a3];
+                }
+                trilinear_corners(vg, px[t], py[t], pz[t], w, off);
 #pragma unroll
-                  for (int q = 0; q < 6; ++q) {
-                    float4 t = __ldg(r4 + q);
-                    smpl[4 * q] = __fadd_rn(smpl[4 * q], __fmul_rn(t.x, w[c]));
-                    smpl[4 * q + 1] = __fadd_rn(smpl[4 * q + 1], __fmul_rn(t.y, w[c]));
-                    smpl[4 * q + 2] = __fadd_rn(smpl[4 * q + 2], __fmul_rn(t.z, w[c]));
-                    smpl[4 * q + 3] = __fadd_rn(smpl[4 * q + 3], __fmul_rn(t.w, w[c]));
+                for (int c = 0; c < 8; ++c) {
+                  if (off[c] >= 0) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)off[c] * ANINERF_N_BONES);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                      float4 w4 = __ldg(r4 + q);
+                      smpl[4 * q] = __fadd_rn(smpl[4 * q], __fmul_rn(w4.x, w[c]));
+                      smpl[4 * q + 1] = __fadd_rn(smpl[4 * q + 1], __fmul_rn(w4.y, w[c]));
+                      smpl[4 * q + 2] = __fadd_rn(smpl[4 * q + 2], __fmul_rn(w4.z, w[c]));
+                      smpl[4 * q + 3] = __fadd_rn(smpl[4 * q + 3], __fmul_rn(w4.w, w[c]));
+                    }
                   }
                 }
               }
             }
           }
-        }
-        ANI_TRACE(8 + 8 * l);
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        ANI_TRACE(8 + 8 * l + 1);
-        const float *bias = s_bias + l * 256;
-        const int n_pad = F.layers[l].n_pad;
-        if (!last) {
-          // hidden layer: bias + ReLU -> bf16 (hi/lo) -> A chunks 8..39 in place
-          const bool alpha_layer = NERF && (l == F.n_layers - 2);
-          for (int g = 0; g < n_pad / 32; ++g) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + g * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float x[8];
-              const float4 b0 = *reinterpret_cast<const float4 *>(bias + g * 32 + q * 8);
-              const float4 b1 = *reinterpret_cast<const float4 *>(bias + g * 32 + q * 8 + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
-              if (alpha_layer) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8);
-                const float4 w1 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8 + 4);
-                sigma = fmaf(x[0], w0.x, sigma);
-                sigma = fmaf(x[1], w0.y, sigma);
-                sigma = fmaf(x[2], w0.z, sigma);
-                sigma = fmaf(x[3], w0.w, sigma);
-                sigma = fmaf(x[4], w1.x, sigma);
-                sigma = fmaf(x[5], w1.y, sigma);
-                sigma = fmaf(x[6], w1.z, sigma);
-                sigma = fmaf(x[7], w1.w, sigma);
+          ANI_TRACE(8 + 16 * l + 8 * t);
+          mbar_wait(bar_acc + 8 * t, acc_phase, 5 + 10 * t + 100 * l);
+          tc_fence_after();
+          ANI_TRACE(8 + 16 * l + 8 * t + 1);
+          if (!last) {
+            if (NERF && l == VIEW_LAYER_WRITE) {
+              // layer 5 was the last reader of PE(xyz): the PE chunks now take PE(viewdir) for the view layer
+              float vx = 0.f, vy = 0.f, vz = 0.f;
+              if (valid[t]) {
+                vx = __ldg(args.viewdir + 3 * gi[t]);
+                vy = __ldg(args.viewdir + 3 * gi[t] + 1);
+                vz = __ldg(args.viewdir + 3 * gi[t] + 2);
               }
-              store_chunk<NPASS>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
+              if (half == 0) write_pe<NPASS, 4, 0, 2>(a_hi, a_lo, PE_CHUNK0, row, vx, vy, vz);
+              else write_pe<NPASS, 4, 2, 4>(a_hi, a_lo, PE_CHUNK0, row, vx, vy, vz);
             }
-          }
-          tc_fence_before();
-          fence_proxy_async();
-          mbar_arrive(bar_a_ready);
-          ANI_TRACE(8 + 8 * l + 2);
-        } else if (!NERF) {
-          // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
-          uint32_t v[32];
-          tmem_ld32(t_lane, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          float bw[ANINERF_N_BONES];
-          float mx = -INFINITY;
+            // hidden layer: bias + ReLU -> bf16 (hi/lo) -> A chunks 8..39 in place; this thread: 128 of the 256 columns
+            const bool alpha_layer = NERF && (l == F.n_layers - 2);
+            const int g0 = half * (n_pad / 64);
+            for (int g = g0; g < g0 + n_pad / 64; ++g) {
+              uint32_t v[32];
+              tmem_ld32(t_acc + g * 32, v);
+              tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < ANINERF_N_BONES; ++k) {
-            bw[k] = logf(smpl[k] + 1e-9f) + (__uint_as_float(v[k]) + bias[k]);
-            mx = fmaxf(mx, bw[k]);
-          }
-          float sum = 0.f;
+              for (int q = 0; q < 4; ++q) {
+                float x[8];
+                const float4 b0 = *reinterpret_cast<const float4 *>(bias + g * 32 + q * 8);
+                const float4 b1 = *reinterpret_cast<const float4 *>(bias + g * 32 + q * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                if (NPASS == 1 && !alpha_layer) {
 #pragma unroll
-          for (int k = 0; k < ANINERF_N_BONES; ++k) {
-            bw[k] = expf(bw[k] - mx);
-            sum += bw[k];
-          }
-          const float inv_sum = 1.0f / sum;
+                  for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[q * 8 + j]) + bb[j];
+                  store_chunk<NPASS, NPASS == 1>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
+                  continue;
+                }
 #pragma unroll
-          for (int k = 0; k < ANINERF_N_BONES; ++k) bw[k] *= inv_sum;
-          if (valid) {
-            if (args.bw_out) {
-              float4 *o4 = reinterpret_cast<float4 *>(args.bw_out + gi * ANINERF_N_BONES);
-#pragma unroll
-              for (int q = 0; q < 6; ++q) o4[q] = make_float4(bw[4 * q], bw[4 * q + 1], bw[4 * q + 2], bw[4 * q + 3]);
+                for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
+                if (alpha_layer) {
+                  const float4 w0 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8);
+                  const float4 w1 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8 + 4);
+                  float sg = sigma[t];
+                  sg = fmaf(x[0], w0.x, sg);
+                  sg = fmaf(x[1], w0.y, sg);
+                  sg = fmaf(x[2], w0.z, sg);
+                  sg = fmaf(x[3], w0.w, sg);
+                  sg = fmaf(x[4], w1.x, sg);
+                  sg = fmaf(x[5], w1.y, sg);
+                  sg = fmaf(x[6], w1.z, sg);
+                  sg = fmaf(x[7], w1.w, sg);
+                  sigma[t] = sg;
+                }
+                store_chunk<NPASS>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
+              }
             }
-            if (args.tpts_out) {
-              float M[12];
+            if (alpha_layer && half == 1) xchg[row * 4] = sigma[t];   // read by the row's other thread after the next acc barrier
+            tc_fence_before();
+            fence_proxy_async();
+            if (leader) mbar_arrive(bar_a_ready + 8 * t);
+            else mbar_arrive_cluster(a_ready_leader + 8 * t);
+            ANI_TRACE(8 + 16 * l + 8 * t + 2);
+          } else if (!NERF) {
+            // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
+            if (half == 0) {
+              uint32_t v[32];
+              tmem_ld32(t_acc, v);
+              tmem_ld_wait();
+              tc_fence_before();
+              float bw[ANINERF_N_BONES];
+              float mx = -INFINITY;
 #pragma unroll
-              for (int j = 0; j < 12; ++j) M[j] = 0.f;
+              for (int k = 0; k < ANINERF_N_BONES; ++k) {
+                bw[k] = logf(smpl[k] + 1e-9f) + (__uint_as_float(v[k]) + bias[k]);
+                mx = fmaxf(mx, bw[k]);
+              }
+              float sum = 0.f;
 #pragma unroll
-              for (int k = 0; k < ANINERF_N_BONES; ++k)
+              for (int k = 0; k < ANINERF_N_BONES; ++k) {
+                bw[k] = expf(bw[k] - mx);
+                sum += bw[k];
+              }
+              const float inv_sum = 1.0f / sum;
 #pragma unroll
-                for (int j = 0; j < 12; ++j) M[j] = fmaf(bw[k], s_head[k * 12 + j], M[j]);
-              float qx = px - M[3], qy = py - M[7], qz = pz - M[11];
-              float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], kk = M[10];
-              float c00 = e * kk - f * h, c01 = c * h - b * kk, c02 = b * f - c * e;
-              float c10 = f * g - d * kk, c11 = a * kk - c * g, c12 = c * d - a * f;
-              float c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
-              float inv = 1.0f / (a * c00 + b * c10 + c * c20);
-              args.tpts_out[3 * gi] = (c00 * qx + c01 * qy + c02 * qz) * inv;
-              args.tpts_out[3 * gi + 1] = (c10 * qx + c11 * qy + c12 * qz) * inv;
-              args.tpts_out[3 * gi + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
-            }
-          }
-        } else {
-          // ---- NeRF head: view layer (ReLU) -> rgb_fc in fp32; alpha from the layer-7 epilogue ---
-          float rgb[3] = {s_head[257 + 384], s_head[257 + 385], s_head[257 + 386]};
-          for (int g = 0; g < n_pad / 32; ++g) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + g * 32, v);
-            tmem_ld_wait();
+              for (int k = 0; k < ANINERF_N_BONES; ++k) bw[k] *= inv_sum;
+              if (valid[t]) {
+                if (args.bw_out) {
+                  float4 *o4 = reinterpret_cast<float4 *>(args.bw_out + gi[t] * ANINERF_N_BONES);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = fmaxf(__uint_as_float(v[j]) + bias[g * 32 + j], 0.f);
-              rgb[0] = fmaf(x, s_head[257 + g * 32 + j], rgb[0]);
-              rgb[1] = fmaf(x, s_head[257 + 128 + g * 32 + j], rgb[1]);
-              rgb[2] = fmaf(x, s_head[257 + 256 + g * 32 + j], rgb[2]);
+                  for (int q = 0; q < 6; ++q) o4[q] = make_float4(bw[4 * q], bw[4 * q + 1], bw[4 * q + 2], bw[4 * q + 3]);
+                }
+                if (args.tpts_out) {
+                  float M[12];
+#pragma unroll
+                  for (int j = 0; j < 12; ++j) M[j] = 0.f;
+#pragma unroll
+                  for (int k = 0; k < ANINERF_N_BONES; ++k)
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) M[j] = fmaf(bw[k], s_head[k * 12 + j], M[j]);
+                  float qx = px[t] - M[3], qy = py[t] - M[7], qz = pz[t] - M[11];
+                  float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], kk = M[10];
+                  float c00 = e * kk - f * h, c01 = c * h - b * kk, c02 = b * f - c * e;
+                  float c10 = f * g - d * kk, c11 = a * kk - c * g, c12 = c * d - a * f;
+                  float c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+                  float inv = 1.0f / (a * c00 + b * c10 + c * c20);
+                  args.tpts_out[3 * gi[t]] = (c00 * qx + c01 * qy + c02 * qz) * inv;
+                  args.tpts_out[3 * gi[t] + 1] = (c10 * qx + c11 * qy + c12 * qz) * inv;
+                  args.tpts_out[3 * gi[t] + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
+                }
+              }
             }
-          }
-          tc_fence_before();
-          sigma += s_head[256];
-          if (valid) {
-            if (args.sigma_out) args.sigma_out[gi] = sigma;
-            if (args.rgb_out) {
-              args.rgb_out[3 * gi] = rgb[0];
-              args.rgb_out[3 * gi + 1] = rgb[1];
-              args.rgb_out[3 * gi + 2] = rgb[2];
+          } else {
+            // ---- NeRF head: view layer (ReLU) -> rgb_fc in fp32; alpha from the layer-7 epilogue ---
+            float rgb[3] = {0.f, 0.f, 0.f};
+            const int g0 = half * (n_pad / 64);
+            for (int g = g0; g < g0 + n_pad / 64; ++g) {
+              uint32_t v[32];
+              tmem_ld32(t_acc + g * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = fmaxf(__uint_as_float(v[j]) + bias[g * 32 + j], 0.f);
+                rgb[0] = fmaf(x, s_head[257 + g * 32 + j], rgb[0]);
+                rgb[1] = fmaf(x, s_head[257 + 128 + g * 32 + j], rgb[1]);
+                rgb[2] = fmaf(x, s_head[257 + 256 + g * 32 + j], rgb[2]);
+              }
             }
-            if (args.raw_out) {
-              // tail of Network.forward (tpose_nerf_network.py:186-212)
-              bool inside = px > args.tbounds[0] && px < args.tbounds[3] && py > args.tbounds[1] && py < args.tbounds[4] &&
-                            pz > args.tbounds[2] && pz < args.tbounds[5];
-              float sg = inside ? sigma : 0.f;
-              if (args.sigma_masked_out) args.sigma_masked_out[gi] = sg;
-              float al = 1.0f - expf(-fmaxf(sg, 0.f) * __ldg(args.dists + gi));
-              float4 o = make_float4(1.0f / (1.0f + expf(-rgb[0])), 1.0f / (1.0f + expf(-rgb[1])), 1.0f / (1.0f + expf(-rgb[2])), al);
-              reinterpret_cast<float4 *>(args.raw_out)[__ldg(args.index + gi)] = o;
+            tc_fence_before();
+            float my_sigma = sigma[t];
+            if (half == 1) {
+              xchg[row * 4 + 1] = rgb[0];
+              xchg[row * 4 + 2] = rgb[1];
+              xchg[row * 4 + 3] = rgb[2];
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // the row's two threads meet
+            if (half == 0) {
+              my_sigma += xchg[row * 4] + s_head[256];
+              rgb[0] += xchg[row * 4 + 1] + s_head[257 + 384];
+              rgb[1] += xchg[row * 4 + 2] + s_head[257 + 385];
+              rgb[2] += xchg[row * 4 + 3] + s_head[257 + 386];
+              if (valid[t]) {
+                const int64_t o = gi[t];
+                if (args.sigma_out) args.sigma_out[o] = my_sigma;
+                if (args.rgb_out) {
+                  args.rgb_out[3 * o] = rgb[0];
+                  args.rgb_out[3 * o + 1] = rgb[1];
+                  args.rgb_out[3 * o + 2] = rgb[2];
+                }
+                if (args.raw_out) {
+                  // tail of Network.forward (tpose_nerf_network.py:186-212)
+                  bool inside = px[t] > args.tbounds[0] && px[t] < args.tbounds[3] && py[t] > args.tbounds[1] && py[t] < args.tbounds[4] &&
+                                pz[t] > args.tbounds[2] && pz[t] < args.tbounds[5];
+                  float sg = inside ? my_sigma : 0.f;
+                  if (args.sigma_masked_out) args.sigma_masked_out[o] = sg;
+                  float al = 1.0f - expf(-fmaxf(sg, 0.f) * __ldg(args.dists + o));
+                  float4 rv = make_float4(1.0f / (1.0f + expf(-rgb[0])), 1.0f / (1.0f + expf(-rgb[1])), 1.0f / (1.0f + expf(-rgb[2])), al);
+                  reinterpret_cast<float4 *>(args.raw_out)[__ldg(args.index + o)] = rv;
+                }
+              }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // s_xchg is rewritten by the next slot / tile
           }
         }
+        acc_phase ^= 1;
       }
     }
   }
@@ -595,9 +799,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   // ---- teardown --------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (PAIR == 2) cluster_sync_all();        // the leader's MMAs read the peer's shared memory: leave together
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc<PAIR>(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -618,10 +823,12 @@ static inline float bf2f(uint16_t h) {
   return f;
 }
 
-struct Segment { int src0, len, pad; };   // source columns [src0, src0+len) zero-padded to `pad`
+// source columns [src0, src0+len) of a layer's weight matrix, zero-padded to `pad` K elements,
+// multiplied against the A chunks starting at `a_chunk0`
+struct Segment { int src0, len, pad, a_chunk0; };
 
 struct HostLayer {
-  int n_out, n_pad, k_in, k_pad, a_chunk0, relu, n_tables;
+  int n_out, n_pad, k_in, relu, n_tables;
   std::vector<Segment> segs;
 };
 
@@ -629,6 +836,7 @@ struct FieldImage {          // per (field, precision)
   uint8_t *image = nullptr;
   Step *steps = nullptr;
   int n_steps = 0;
+  int step0[MAX_LAYERS] = {0}, n_layer_steps[MAX_LAYERS] = {0};
 };
 
 struct FieldHost {
@@ -647,6 +855,9 @@ struct aninerf_net {
 };
 
 namespace aninerf {
+
+// CTAs per tcgen05.mma (cta_group): CTA pairs, each CTA holds half of every weight chunk
+constexpr int kPair = 2;
 
 static void free_field(FieldHost &f) {
   cudaFree(f.bias);
@@ -671,70 +882,72 @@ static int describe_layers(int field, const aninerf_layer *L, int n_layers, std:
     h.n_tables = L[l].n_tables;
     int want_k, want_n;
     if (l == 0) {
-      want_k = 63; want_n = 256; h.segs = {{0, 63, 64}}; h.a_chunk0 = PE_CHUNK0;
-    } else if (l == 5) {
-      want_k = 63 + 256; want_n = 256; h.segs = {{0, 63, 64}, {63, 256, 256}}; h.a_chunk0 = PE_CHUNK0;
+      want_k = 63; want_n = 256; h.segs = {{0, 63, 64, PE_CHUNK0}};
+    } else if (l == 5) {     // skip layer: [PE(xyz), hidden]
+      want_k = 63 + 256; want_n = 256; h.segs = {{0, 63, 64, PE_CHUNK0}, {63, 256, 256, HID_CHUNK0}};
     } else if (l < 8) {
-      want_k = 256; want_n = 256; h.segs = {{0, 256, 256}}; h.a_chunk0 = HID_CHUNK0;
-    } else if (nerf) {
-      want_k = 256 + 27; want_n = 128; h.segs = {{0, 256, 256}, {256, 27, 32}}; h.a_chunk0 = HID_CHUNK0;
+      want_k = 256; want_n = 256; h.segs = {{0, 256, 256, HID_CHUNK0}};
+    } else if (nerf) {       // folded view layer: [hidden, PE(viewdir)]; PE(viewdir) sits in the old PE(xyz) chunks
+      want_k = 256 + 27; want_n = 128; h.segs = {{256, 27, 32, PE_CHUNK0}, {0, 256, 256, HID_CHUNK0}};
     } else {
-      want_k = 256; want_n = ANINERF_N_BONES; h.segs = {{0, 256, 256}}; h.a_chunk0 = HID_CHUNK0;
+      want_k = 256; want_n = ANINERF_N_BONES; h.segs = {{0, 256, 256, HID_CHUNK0}};
     }
     if (h.k_in != want_k || h.n_out != want_n || !L[l].W || !L[l].bias_table || h.n_tables < 1)
       return fail(ANINERF_EINVAL, "%s: layer shape does not match the aninerf architecture%s", "aninerf_net_load_field");
     h.n_pad = (h.n_out + 31) / 32 * 32;
-    h.k_pad = 0;
-    for (auto &s : h.segs) h.k_pad += s.pad;
     out.push_back(h);
   }
   return ANINERF_OK;
 }
 
 static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, int npass, FieldImage &im, cudaStream_t st) {
-  const int hi_max = npass == 3 ? STAGE_BYTES / 2 : STAGE_BYTES;
+  const int hi_max = npass == 3 ? STAGE_BYTES / 2 : STAGE_BYTES;   // per CTA
   std::vector<Step> steps;
   std::vector<uint8_t> image;
   for (size_t l = 0; l < H.size(); ++l) {
     const HostLayer &h = H[l];
-    // padded-K -> source column map
-    std::vector<int> col(h.k_pad, -1);
-    int kp = 0;
-    for (auto &s : h.segs) {
-      for (int j = 0; j < s.len; ++j) col[kp + j] = s.src0 + j;
-      kp += s.pad;
+    const int n_half = h.n_pad / kPair;                     // weight rows held by each CTA of the pair
+    const int per_step = std::max(1, hi_max / (n_half * 32));
+    im.step0[l] = (int)steps.size();
+    for (size_t si = 0; si < h.segs.size(); ++si) {
+      const Segment &sg = h.segs[si];
+      const int k16_total = sg.pad / 16;
+      for (int k0 = 0; k0 < k16_total; k0 += per_step) {
+        const int nk = std::min(per_step, k16_total - k0);
+        Step s;
+        s.w_off = (uint32_t)image.size();
+        const size_t hi_bytes = (size_t)nk * 2 * n_half * 16;            // per CTA
+        const size_t cta_bytes = hi_bytes * (npass == 3 ? 2 : 1);
+        s.bytes = (uint32_t)(cta_bytes * kPair);
+        s.a_chunk = (uint16_t)(sg.a_chunk0 + 2 * k0);
+        s.n_k16 = (uint16_t)nk;
+        s.layer = (uint16_t)l;
+        s.flags = (uint16_t)(((si == 0 && k0 == 0) ? 1 : 0) | ((si + 1 == h.segs.size() && k0 + nk >= k16_total) ? 2 : 0));
+        image.resize(image.size() + s.bytes, 0);
+        for (int r = 0; r < kPair; ++r) {           // image = [CTA0: hi, lo][CTA1: hi, lo]
+          uint16_t *hi = reinterpret_cast<uint16_t *>(image.data() + s.w_off + r * cta_bytes);
+          uint16_t *lo = reinterpret_cast<uint16_t *>(image.data() + s.w_off + r * cta_bytes + hi_bytes);
+          for (int c = 0; c < nk * 2; ++c)          // 8-wide K chunk
+            for (int nn = 0; nn < n_half; ++nn)
+              for (int j = 0; j < 8; ++j) {
+                const int n = r * n_half + nn;
+                const int k = (k0 * 2 + c) * 8 + j;         // K index inside the segment
+                float w = 0.f;
+                if (n < h.n_out && k < sg.len) w = L[l].W[(size_t)n * h.k_in + sg.src0 + k];
+                const uint16_t wh = f2bf(w);
+                const size_t o = ((size_t)c * n_half + nn) * 8 + j;
+                hi[o] = wh;
+                if (npass == 3) lo[o] = f2bf(w - bf2f(wh));
+              }
+        }
+        steps.push_back(s);
+      }
     }
-    const int k16_total = h.k_pad / 16;
-    const int per_step = std::max(1, hi_max / (h.n_pad * 32));
-    for (int k0 = 0; k0 < k16_total; k0 += per_step) {
-      const int nk = std::min(per_step, k16_total - k0);
-      Step s;
-      s.w_off = (uint32_t)image.size();
-      const size_t hi_bytes = (size_t)nk * 2 * h.n_pad * 16;
-      s.bytes = (uint32_t)(hi_bytes * (npass == 3 ? 2 : 1));
-      s.a_chunk = (uint16_t)(h.a_chunk0 + 2 * k0);
-      s.n_k16 = (uint16_t)nk;
-      s.layer = (uint16_t)l;
-      s.flags = (uint16_t)((k0 == 0 ? 1 : 0) | (k0 + nk >= k16_total ? 2 : 0));
-      image.resize(image.size() + s.bytes, 0);
-      uint16_t *hi = reinterpret_cast<uint16_t *>(image.data() + s.w_off);
-      uint16_t *lo = reinterpret_cast<uint16_t *>(image.data() + s.w_off + hi_bytes);
-      for (int c = 0; c < nk * 2; ++c)          // 8-wide K chunk
-        for (int n = 0; n < h.n_pad; ++n)
-          for (int j = 0; j < 8; ++j) {
-            int k = (k0 * 2 + c) * 8 + j;
-            float w = 0.f;
-            if (n < h.n_out && col[k] >= 0) w = L[l].W[(size_t)n * h.k_in + col[k]];
-            uint16_t wh = f2bf(w);
-            size_t o = ((size_t)c * h.n_pad + n) * 8 + j;
-            hi[o] = wh;
-            if (npass == 3) lo[o] = f2bf(w - bf2f(wh));
-          }
-      steps.push_back(s);
-    }
+    im.n_layer_steps[l] = (int)steps.size() - im.step0[l];
   }
+  if (steps.size() > (size_t)MAX_STEPS) return fail(ANINERF_EINVAL, "%s: internal: too many steps%s", __func__);
   for (auto &s : steps)
-    if (s.bytes > (uint32_t)STAGE_BYTES || (s.bytes & 15u)) return fail(ANINERF_EINVAL, "%s: internal: bad step size%s", __func__);
+    if (s.bytes / kPair > (uint32_t)STAGE_BYTES || ((s.bytes / kPair) & 15u)) return fail(ANINERF_EINVAL, "%s: internal: bad step size%s", __func__);
   ANI_CUDA(cudaMalloc(&im.image, image.size()));
   ANI_CUDA(cudaMalloc(&im.steps, steps.size() * sizeof(Step)));
   ANI_CUDA(cudaMemcpyAsync(im.image, image.data(), image.size(), cudaMemcpyHostToDevice, st));
@@ -744,23 +957,34 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
   return ANINERF_OK;
 }
 
-template <int NPASS, bool NERF>
+template <int NPASS, bool NERF, int NT>
 static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
-  using C = Cfg<NPASS, NERF>;
+  using C = Cfg<NPASS, NERF, NT>;
   static bool configured = false;
   if (!configured) {
-    ANI_CUDA(cudaFuncSetAttribute(mlp_kernel<NPASS, NERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    ANI_CUDA(cudaFuncSetAttribute(mlp_kernel<NPASS, NERF, kPair, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
-  int64_t tiles = (a.n + TILE_M - 1) / TILE_M;
-  int grid = (int)std::min<int64_t>(tiles, sm_count());
-  if (grid <= 0) return ANINERF_OK;
-  mlp_kernel<NPASS, NERF><<<grid, N_THREADS, C::SMEM, st>>>(a);
+  const int64_t rows_per_unit = (int64_t)TILE_M * kPair * NT;
+  const int64_t utiles = (a.n + rows_per_unit - 1) / rows_per_unit;
+  const int units = (int)std::min<int64_t>(utiles, sm_count() / kPair);
+  if (units <= 0) return ANINERF_OK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(units * kPair));
+  cfg.blockDim = dim3(N_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ANI_CUDA(cudaLaunchKernelEx(&cfg, mlp_kernel<NPASS, NERF, kPair, NT>, a));
   ANI_LAUNCHED();
   return ANINERF_OK;
 }
-
-
 
 static unsigned long long *g_trace = nullptr;
 
@@ -776,6 +1000,10 @@ static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs 
   a.f.n_steps = im.n_steps;
   a.f.n_layers = f.n_layers;
   memcpy(a.f.layers, f.layers, sizeof(f.layers));
+  for (int l = 0; l < f.n_layers; ++l) {
+    a.f.layers[l].step0 = im.step0[l];
+    a.f.layers[l].n_steps = im.n_layer_steps[l];
+  }
   a.f.bias = f.bias;
   a.f.head = f.head;
   a.trace = g_trace;
@@ -803,7 +1031,7 @@ int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *
   a.A = A;
   a.bw_out = bw_out;
   a.tpts_out = tpts_out;
-  return precision == 3 ? launch_mlp<3, false>(a, st) : launch_mlp<1, false>(a, st);
+  return precision == 3 ? launch_mlp<3, false, 1>(a, st) : launch_mlp<1, false, 2>(a, st);
 }
 
 int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
@@ -825,7 +1053,7 @@ int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, cons
   a.index = index;
   a.raw_out = raw_out;
   a.sigma_masked_out = sigma_masked_out;
-  return precision == 3 ? launch_mlp<3, true>(a, st) : launch_mlp<1, true>(a, st);
+  return precision == 3 ? launch_mlp<3, true, 1>(a, st) : launch_mlp<1, true, 2>(a, st);
 }
 
 }  // namespace aninerf

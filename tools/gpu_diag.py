@@ -152,9 +152,20 @@ def trace():
         t0 = t[0]
         say(f'{name}: tile start 0, PE done {t[1] - t0}')
         for l in range(9):
-            b = 8 + 8 * l
-            say(f'  L{l}: mma wait_a {t[b + 4] - t0} woke {t[b + 5] - t0} issued {t[b + 6] - t0} | rows wait {t[b] - t0} woke {t[b + 1] - t0} '
-                f'done {t[b + 2] - t0 if t[b + 2] else 0}  || mma phase {t[b + 1] - t[b + 5]} (issue {t[b + 6] - t[b + 5]}) epilogue {t[b + 2] - t[b + 1] if t[b + 2] else 0}')
+            for ts in range(2):
+                b = 8 + 16 * l + 8 * ts
+                if t[b + 5] == 0:
+                    continue
+                say(f'  L{l} slot{ts}: mma wait_a {t[b + 4] - t0} woke {t[b + 5] - t0} issued {t[b + 6] - t0} | rows wait {t[b] - t0} '
+                    f'woke {t[b + 1] - t0} done {t[b + 2] - t0 if t[b + 2] else 0}  || issue {t[b + 6] - t[b + 5]} '
+                    f'epilogue {t[b + 2] - t[b + 1] if t[b + 2] else 0}')
+        for ts in range(2):
+            for i in range(12):
+                b = 160 + 48 * ts + 4 * i
+                if t[b] == 0:
+                    continue
+                say(f'    L2 slot{ts} step{i}: wait {t[b + 1] - t[b]} issue {t[b + 2] - t[b + 1]} commit {t[b + 3] - t[b + 2]} '
+                    f'(t={t[b] - t0}..{t[b + 3] - t0})')
 
 
 if 'trace' in sys.argv[1:]:
