@@ -276,15 +276,29 @@ __global__ void __launch_bounds__(256) sample_bw_kernel(const float *__restrict_
     int off[8];
     if (mine < n) trilinear_corners(g, pts[3 * mine], pts[3 * mine + 1], pts[3 * mine + 2], w, off);
     int cnt = (int)min((int64_t)32, n - base);
-    for (int p = 0; p < cnt; ++p) {
-      float acc = 0.f;
+    // four points per trip: 32 independent corner-row loads in flight per warp
+    for (int p0 = 0; p0 < cnt; p0 += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float v[4][8];
+      float wk[4][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float wk = __shfl_sync(0xffffffffu, w[k], p);
-        int ok = __shfl_sync(0xffffffffu, off[k], p);
-        if (ok >= 0 && lane < ANINERF_BW_CH) acc = __fadd_rn(acc, __fmul_rn(__ldg(vol + (int64_t)ok * ANINERF_BW_CH + lane), wk));
+      for (int u = 0; u < 4; ++u) {
+        const int p = min(p0 + u, cnt - 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          wk[u][k] = __shfl_sync(0xffffffffu, w[k], p);
+          const int ok = __shfl_sync(0xffffffffu, off[k], p);
+          v[u][k] = (ok >= 0 && lane < ANINERF_BW_CH) ? __ldg(vol + (int64_t)ok * ANINERF_BW_CH + lane) : 0.f;
+          if (ok < 0) wk[u][k] = -1.f;           // marks "corner outside": skipped, as ATen does
+        }
       }
-      if (lane < ANINERF_BW_CH) out[(base + p) * ANINERF_BW_CH + lane] = acc;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (wk[u][k] >= 0.f) acc[u] = __fadd_rn(acc[u], __fmul_rn(v[u][k], wk[u][k]));
+        if (p0 + u < cnt && lane < ANINERF_BW_CH) out[(base + p0 + u) * ANINERF_BW_CH + lane] = acc[u];
+      }
     }
   }
 }

@@ -142,6 +142,69 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# stand-alone stage kernels vs the HBM roofline (north_star: LBS / grid sampling / compositing)
+# ------------------------------------------------------------------------------------------------
+def stage_kernel_rooflines(dev, frame, hbm_gbs, ray_pts=None):
+    """Each stage kernel alone through its C-ABI entry, on inputs larger than the 126 MB L2, CUDA-event timed.
+    Algorithmic bytes per unit from SURVEY.md 8d: volume sampling 112 B/pt, inverse LBS 120 B/pt,
+    compositing 1300 B/ray."""
+    import ctypes as C
+    from animatable_nerf_b200 import _lib
+    L = _lib.lib()
+    st = _lib.stream_ptr(dev)
+    g = torch.Generator(device='cpu').manual_seed(0)
+    out = {}
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        evs = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    def entry(name, ms, units, bytes_per_unit, unit_name):
+        gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
+        out[name] = {'ms': ms, 'units': units, 'unit': unit_name, 'algorithmic_bytes_per_unit': bytes_per_unit, 'achieved_gbs': gbs,
+                     'peak_gbs': hbm_gbs, 'frac': gbs / hbm_gbs}
+
+    n = 4 << 20
+    # inverse LBS: 12 + 96 B in, 12 B out per point
+    pts = (torch.rand(n, 3, generator=g) - 0.5).to(dev)
+    bw = torch.softmax(torch.randn(n, 24, generator=g), dim=1).to(dev)
+    A = torch.as_tensor(frame['A']).to(dev)
+    tp = torch.empty(n, 3, device=dev)
+    entry('inverse_lbs', timeit(lambda: _lib.check(L.aninerf_inverse_lbs(_lib.ptr(pts), _lib.ptr(bw), n, _lib.ptr(A), _lib.ptr(tp), st))),
+          n, 120, 'points')
+    # blend-weight volume sampling: 12 B in, 100 B out per point (+ the L2-resident volume)
+    vol = torch.as_tensor(frame['pbw']).to(dev)
+    pb = torch.as_tensor(frame['pbounds']).to(dev)
+    if ray_pts is not None and ray_pts.shape[0] >= n:
+        q = ray_pts[:n].contiguous()              # consecutive samples along real rays of the frame (the path's access pattern)
+    else:
+        lo, hi = torch.as_tensor(frame['pbounds'][0]), torch.as_tensor(frame['pbounds'][1])
+        q = (torch.rand(n, 3, generator=g) * (hi - lo) + lo).to(dev)
+    o25 = torch.empty(n, 25, device=dev)
+    dims = (C.c_int32 * 3)(*vol.shape[:3])
+    entry('sample_blend_weights', timeit(lambda: _lib.check(L.aninerf_sample_blend_weights(_lib.ptr(q), n, _lib.ptr(vol), dims, _lib.ptr(pb),
+                                                                                           _lib.ptr(o25), st))), n, 112, 'points')
+    del o25, bw
+    # compositing: (16 + 4) B x 64 in, 20 B out per ray
+    R = 1 << 20
+    raw = torch.rand(R, 64, 4, generator=g).to(dev)
+    z = torch.sort(torch.rand(R, 64, generator=g) + 2.0, dim=1)[0].to(dev)
+    rgb, acc, dep = torch.empty(R, 3, device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev)
+    entry('composite', timeit(lambda: _lib.check(L.aninerf_composite(_lib.ptr(raw), _lib.ptr(z), R, 64, 0, _lib.ptr(rgb), _lib.ptr(acc),
+                                                                     _lib.ptr(dep), None, None, st))), R, 1300, 'rays')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -276,6 +339,18 @@ def run_b200(args):
         'stage_ms_rank0': stage_ms,
         'active_samples_per_s': n_active_total / (ms_per_step * 1e-3),
     }
+    if rank == 0 and world == 1:
+        # pose-space sample points of the first 65536 rays of the frame, in ray order
+        import ctypes as C
+        nr = min(n_rays, 65536)
+        wp = torch.empty(nr * S, 3, device=dev)
+        _lib.check(L.aninerf_sample_points(_lib.ptr(full['ray_o'][0]), _lib.ptr(full['ray_d'][0]), _lib.ptr(full['near'][0]),
+                                           _lib.ptr(full['far'][0]), _lib.ptr(renderer._tv(S, dev)), None, nr, S, _lib.ptr(wp), None, None,
+                                           _lib.stream_ptr(dev)))
+        pp = torch.empty_like(wp)
+        _lib.check(L.aninerf_world_to_pose(_lib.ptr(wp), nr * S, _lib.ptr(full['R'][0]), _lib.ptr(full['Th'][0]), _lib.ptr(pp),
+                                           _lib.stream_ptr(dev)))
+        line['stage_kernels'] = stage_kernel_rooflines(dev, frame, pk['hbm_gbs'], ray_pts=pp)
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, sec, n = cpu_render_rate(frame, cam, sd, args.size, reps=3)
         line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': os.cpu_count() or 1, 'kind': 'port',

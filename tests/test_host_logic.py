@@ -1,0 +1,124 @@
+"""CPU: host-side logic of the drop-in -- weight folding, row selection, ray-tile sharding, batch schema."""
+import numpy as np
+import torch
+
+from helpers import O, golden_small_case
+from animatable_nerf_b200 import config, ray_tiles, synthetic, weights
+from animatable_nerf_b200.tpose_nerf_network import Network
+from animatable_nerf_b200.tpose_renderer import select_forced_argmax
+
+
+def _run_layers(layers, x, final_relu):
+    h = x
+    for i, (W, b) in enumerate(layers):
+        h = h @ W.T + b
+        if i < len(layers) - 1 or final_relu:
+            h = np.maximum(h, 0)
+    return h
+
+
+def test_network_mirror_has_the_reference_checkpoint_layout():
+    sd = synthetic.make_state_dict(seed=0, num_train_frame=60, num_eval_frame=7)
+    net = Network(config.make_cfg(aninerf_animation=True, num_eval_frame=7))
+    assert sum(p.numel() for p in Network(config.make_cfg()).parameters()) == 1274652
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+
+
+def test_blend_weight_field_folding_matches_oracle():
+    """latent folded into per-index bias tables == the reference's concat-then-conv (fp64 vs fp32 noise only)"""
+    sd = synthetic.make_state_dict(seed=3)
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(1, 257, 3, generator=g) * 2 - 1
+    smpl = torch.softmax(torch.randn(1, 24, 257, generator=g), dim=1)
+    for idx in (0, 5, 60):
+        ref = O.neural_blend_weights(sd, pts, smpl, torch.tensor([idx]))
+        layers = weights.fold_bw_field(sd)
+        assert [w.shape for w, _ in layers] == [(256, 63)] + [(256, 256)] * 4 + [(256, 319)] + [(256, 256)] * 2 + [(24, 256)]
+        pe = O.positional_encoding(pts, 10)[0].double().numpy()
+        h = pe
+        for i, (W, b) in enumerate(layers[:8]):
+            inp = np.concatenate([pe, h], axis=1) if i == 5 else h
+            h = np.maximum(inp @ W.T + b[min(idx, len(b) - 1)], 0)
+        logits = h @ layers[8][0].T + layers[8][1][0] + np.log(smpl[0].t().double().numpy() + 1e-9)
+        bw = torch.softmax(torch.from_numpy(logits), dim=1).t()[None]
+        assert float((bw - ref.double()).abs().max()) < 5e-6
+
+
+def test_nerf_field_folding_matches_oracle():
+    """feature_fc o latent_fc o view_fc collapsed into one (256+27)->128 layer with per-frame bias"""
+    sd = synthetic.make_state_dict(seed=4)
+    g = torch.Generator().manual_seed(1)
+    pts = torch.rand(1, 129, 3, generator=g) * 2 - 1
+    vd = torch.nn.functional.normalize(torch.randn(1, 129, 3, generator=g), dim=2)
+    for idx in (0, 17):
+        alpha, rgb = O.nerf_alpha_rgb(sd, pts, vd, torch.tensor([idx]))
+        layers, (aw, ab, rw, rb) = weights.fold_nerf_field(sd)
+        assert layers[8][0].shape == (128, 283) and layers[8][1].shape == (60, 128)
+        pe = O.positional_encoding(pts, 10)[0].double().numpy()
+        pv = O.positional_encoding(vd, 4)[0].double().numpy()
+        h = pe
+        for i, (W, b) in enumerate(layers[:8]):
+            inp = np.concatenate([pe, h], axis=1) if i == 5 else h
+            h = np.maximum(inp @ W.T + b[0], 0)
+        a = h @ aw.T + ab
+        v = np.maximum(np.concatenate([h, pv], axis=1) @ layers[8][0].T + layers[8][1][idx], 0)
+        c = v @ rw.T + rb
+        assert np.abs(a[:, 0] - alpha[0, 0].double().numpy()).max() < 1e-5
+        assert np.abs(c.T - rgb[0].double().numpy()).max() < 1e-5
+
+
+def test_select_forced_argmax_matches_per_chunk_loop():
+    g = torch.Generator().manual_seed(2)
+    counts = torch.tensor([5, 1, 40, 7, 3])
+    off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]).int()
+    sig = torch.randn(int(counts.sum()), generator=g)
+    sig[5] = -3.0                      # single-row chunk below the threshold: must still be kept
+    sig[6:46] = -1.0                   # a whole chunk below threshold with ties: first row wins
+    got = select_forced_argmax(sig, off, 0.0)
+    want = sig > 0
+    for c in range(len(counts)):
+        a, b = int(off[c]), int(off[c + 1])
+        want[a + int(torch.argmax(sig[a:b]))] = True
+    assert torch.equal(got, want)
+
+
+def test_ray_tiles_partition_is_a_permutation_aligned_to_chunks():
+    for n_rays in (1, 2047, 2048, 2049, 242907):
+        for world in (1, 2, 4, 8):
+            parts = [ray_tiles.shard_indices(n_rays, r, world) for r in range(world)]
+            allidx = torch.cat(parts)
+            assert allidx.numel() == n_rays and torch.equal(torch.sort(allidx)[0], torch.arange(n_rays))
+            assert ray_tiles.shard_sizes(n_rays, world) == [p.numel() for p in parts]
+            for p in parts:                      # every piece is a run of whole reference chunks
+                if p.numel():
+                    starts = p[torch.cat([torch.tensor([True]), p[1:] != p[:-1] + 1])]
+                    assert bool((starts % ray_tiles.CHUNK == 0).all())
+
+
+def test_sharded_oracle_render_equals_unsharded():
+    """Chunk-aligned shards reproduce the 1-rank result exactly (per-chunk argmin forcing is shard-local)."""
+    _, batch, sd = golden_small_case()
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0.))
+    n = batch['ray_o'].shape[1]
+    out = torch.empty(n, 3)
+    for r in range(2):
+        sb = ray_tiles.shard_batch(batch, r, 2)
+        part = O.render(sd, sb, O.OracleCfg(perturb=0.))
+        out[ray_tiles.shard_indices(n, r, 2)] = part['rgb_map'][0]
+    assert torch.equal(out, ref['rgb_map'][0])
+
+
+def test_synthetic_batch_schema():
+    frame = synthetic.make_frame(voxel=0.1)
+    K, R, T = synthetic.make_camera(frame, 32, 32, focal=33.0)
+    ray_o, ray_d, near, far, mask = O.get_rays_within_bounds(32, 32, K, R, T, frame['wbounds'])
+    b = synthetic.make_render_batch(frame, ray_o, ray_d, near, far)
+    n = ray_o.shape[0]
+    assert b['ray_o'].shape == (1, n, 3) and b['near'].shape == (1, n) and b['occupancy'].dtype == torch.uint8
+    assert b['A'].shape == (1, 24, 4, 4) and b['pbw'].shape[-1] == 25 and b['tbw'].shape[-1] == 25
+    assert b['pbounds'].shape == (1, 2, 3) and b['R'].shape == (1, 3, 3) and b['Th'].shape == (1, 1, 3)
+    assert b['latent_index'].dtype == torch.int64
+    # skinning weights in the volumes are convex combinations
+    assert torch.allclose(b['pbw'][..., :24].sum(-1), torch.ones_like(b['pbw'][..., 0]), atol=1e-5)
