@@ -102,7 +102,7 @@ __device__ __forceinline__ void trilinear_corners(const VolumeGrid &g, float px,
     float n = __fdiv_rn(__fsub_rn(c[a], g.lo[a]), g.ext[a]);          // (p - min) / (max - min)
     n = __fsub_rn(__fmul_rn(n, 2.0f), 1.0f);                          // * 2 - 1
     float lim = (float)(g.dim[a] - 1);
-    float u = __fmul_rn(__fdiv_rn(__fadd_rn(n, 1.0f), 2.0f), lim);    // ((c+1)/2) * (size-1)
+    float u = __fmul_rn(__fmul_rn(__fadd_rn(n, 1.0f), 0.5f), lim);    // ((c+1)/2) * (size-1); x*0.5 == x/2 exactly
     u = fminf(lim, fmaxf(u, 0.0f));                                   // border clip
     float f = floorf(u);
     i0[a] = (int)f;

@@ -276,29 +276,15 @@ __global__ void __launch_bounds__(256) sample_bw_kernel(const float *__restrict_
     int off[8];
     if (mine < n) trilinear_corners(g, pts[3 * mine], pts[3 * mine + 1], pts[3 * mine + 2], w, off);
     int cnt = (int)min((int64_t)32, n - base);
-    // four points per trip: 32 independent corner-row loads in flight per warp
-    for (int p0 = 0; p0 < cnt; p0 += 4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      float v[4][8];
-      float wk[4][8];
+    for (int p = 0; p < cnt; ++p) {
+      float acc = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int p = min(p0 + u, cnt - 1);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          wk[u][k] = __shfl_sync(0xffffffffu, w[k], p);
-          const int ok = __shfl_sync(0xffffffffu, off[k], p);
-          v[u][k] = (ok >= 0 && lane < ANINERF_BW_CH) ? __ldg(vol + (int64_t)ok * ANINERF_BW_CH + lane) : 0.f;
-          if (ok < 0) wk[u][k] = -1.f;           // marks "corner outside": skipped, as ATen does
-        }
+      for (int k = 0; k < 8; ++k) {
+        float wk = __shfl_sync(0xffffffffu, w[k], p);
+        int ok = __shfl_sync(0xffffffffu, off[k], p);
+        if (ok >= 0 && lane < ANINERF_BW_CH) acc = __fadd_rn(acc, __fmul_rn(__ldg(vol + (int64_t)ok * ANINERF_BW_CH + lane), wk));
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (wk[u][k] >= 0.f) acc[u] = __fadd_rn(acc[u], __fmul_rn(v[u][k], wk[u][k]));
-        if (p0 + u < cnt && lane < ANINERF_BW_CH) out[(base + p0 + u) * ANINERF_BW_CH + lane] = acc[u];
-      }
+      if (lane < ANINERF_BW_CH) out[(base + p) * ANINERF_BW_CH + lane] = acc;
     }
   }
 }
@@ -493,18 +479,20 @@ __global__ void __launch_bounds__(256) mask_kernel(SampleSetup p, const float *_
     s1mt[threadIdx.x] = __fsub_rn(1.0f, t);
   }
   __syncthreads();
-  int64_t n = p.n_rays * p.S;
-  int64_t base = (int64_t)blockIdx.x * MB;
+  const uint32_t n = (uint32_t)(p.n_rays * p.S);            // < 2^31 (checked by the host)
+  const uint32_t base = blockIdx.x * (uint32_t)MB;
+  const int log2S = p.S == 64 ? 6 : 5;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int cnt = 0;
   unsigned long long best = ~0ull;
+  const uint32_t chunk_base = base % (uint32_t)chunk_samples;   // blocks never straddle chunks
 #pragma unroll 2
   for (int it = 0; it < MB / 256; ++it) {
-    int64_t i = base + it * 256 + threadIdx.x;
+    const uint32_t i = base + it * 256 + threadIdx.x;
     bool act = false;
     if (i < n) {
-      int64_t r = i / p.S;
-      int s = (int)(i - r * p.S);
+      const int64_t r = i >> log2S;
+      const int s = (int)(i & (uint32_t)(p.S - 1));
       float z, wx, wy, wz, px, py, pz;
       sample_at(p, st, s1mt, r, s, z, wx, wy, wz);
       world_to_pose(s_frame, wx, wy, wz, px, py, pz);
@@ -516,7 +504,7 @@ __global__ void __launch_bounds__(256) mask_kernel(SampleSetup p, const float *_
       for (int k = 0; k < 8; ++k)
         if (off[k] >= 0) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
       act = pn < p.norm_th;
-      unsigned long long key = ((unsigned long long)float_key(pn) << 32) | (unsigned long long)(uint32_t)(i % chunk_samples);
+      unsigned long long key = ((unsigned long long)float_key(pn) << 32) | (unsigned long long)(chunk_base + it * 256 + threadIdx.x);
       best = key < best ? key : best;
     }
     unsigned bal = __ballot_sync(0xffffffffu, act);

@@ -45,19 +45,36 @@ def shard_batch(batch: dict, rank: int, world: int, chunk: int = CHUNK) -> dict:
     return out
 
 
+_PLANS = {}
+
+
+def gather_plan(n_rays: int, world: int, chunk: int = CHUNK, device='cpu'):
+    """(pad, pos): pad = rows every rank contributes to the all-gather; pos[i] = row of frame ray i in the
+    gathered (world*pad, C) buffer.  Cached: a sweep renders many frames with the same ray count."""
+    key = (n_rays, world, chunk, str(device))
+    if key not in _PLANS:
+        sizes = shard_sizes(n_rays, world, chunk)
+        pad = max(sizes)
+        pos = torch.empty(n_rays, dtype=torch.long)
+        for r in range(world):
+            idx = shard_indices(n_rays, r, world, chunk)
+            pos[idx] = r * pad + torch.arange(sizes[r])
+        _PLANS[key] = (pad, pos.to(device))
+    return _PLANS[key]
+
+
 def gather_maps(local: torch.Tensor, n_rays: int, rank: int, world: int, chunk: int = CHUNK, group=None) -> torch.Tensor:
-    """All-gather per-ray rows (R_local, C) from every rank and put them back in frame order -> (n_rays, C)."""
+    """All-gather per-ray rows (R_local, C) from every rank and put them back in frame order -> (n_rays, C).
+    One collective (NCCL all_gather over NVLink, 20 B/ray for rgb+acc+depth) and one gather kernel."""
     if world == 1:
         return local
-    sizes = shard_sizes(n_rays, world, chunk)
-    pad = max(sizes)
+    pad, pos = gather_plan(n_rays, world, chunk, local.device)
     C = local.shape[1]
-    send = torch.zeros(pad, C, dtype=local.dtype, device=local.device)
-    send[:local.shape[0]] = local
+    if local.shape[0] == pad:
+        send = local.contiguous()
+    else:
+        send = torch.zeros(pad, C, dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
     recv = torch.empty(world * pad, C, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(recv, send, group=group)
-    full = torch.empty(n_rays, C, dtype=local.dtype, device=local.device)
-    for r in range(world):
-        idx = shard_indices(n_rays, r, world, chunk, device=local.device)
-        full[idx] = recv[r * pad:r * pad + sizes[r]]
-    return full
+    return recv.index_select(0, pos)

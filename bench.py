@@ -285,6 +285,14 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         out, _ = step_device()
         step_e2e()
+    identical = None
+    if world > 1:
+        # the N-GPU image must be bit-identical to the 1-GPU image of the same kernels
+        _, img_n = step_device()
+        if rank == 0:
+            o1 = renderer.render_device(full, want_bw=False)
+            img_1 = torch.cat([o1['rgb_map'], o1['acc_map'][:, None], o1['depth_map'][:, None]], dim=1)
+            identical = bool(torch.equal(img_1, img_n))
     n_active = int(out['n_active'].item())
     na = torch.tensor([n_active], dtype=torch.int64, device=dev)
     if world > 1:
@@ -338,6 +346,7 @@ def run_b200(args):
         'roofline': roofline,
         'stage_ms_rank0': stage_ms,
         'active_samples_per_s': n_active_total / (ms_per_step * 1e-3),
+        'bit_identical_to_1gpu': identical,
     }
     if rank == 0 and world == 1:
         # pose-space sample points of the first 65536 rays of the frame, in ray order
