@@ -36,7 +36,8 @@ class Layer(C.Structure):
 class Frame(C.Structure):
     _fields_ = [('A', C.c_void_p), ('R', C.c_void_p), ('Th', C.c_void_p), ('pbw', C.c_void_p), ('tbw', C.c_void_p),
                 ('pbounds', C.c_void_p), ('tbounds', C.c_void_p), ('pbw_dims', C.c_int32 * 3), ('tbw_dims', C.c_int32 * 3),
-                ('latent_index', C.c_int32), ('bw_latent_index', C.c_int32)]
+                ('latent_index', C.c_int32), ('bw_latent_index', C.c_int32), ('latent_index_dev', C.c_void_p),
+                ('bw_latent_index_dev', C.c_void_p)]
 
 
 class RenderParams(C.Structure):

@@ -78,6 +78,7 @@ struct FieldDev {
 struct MlpArgs {
   FieldDev f;
   int32_t latent_index;
+  const int64_t *latent_dev;   // optional device int64 (batch['latent_index'] as the reference holds it): index = *latent_dev + latent_index
   const float *pts;        // (n,3)
   const float *viewdir;    // (n,3) NeRF
   int64_t n;
@@ -316,11 +317,23 @@ __device__ __forceinline__ void write_pe(uint8_t *a_hi, uint8_t *a_lo, int chunk
   constexpr int F1 = ((J1 < NV ? J1 : NV) - 1 - 3) / 6;           // last frequency touched
   const float p[3] = {px, py, pz};
   float sn[F1 - F0 + 1][3], cs[F1 - F0 + 1][3];
+  // sin / cos of 2^f * x for power-of-two frequencies: x / 2pi once, in double-float (Cody-Waite split of 1/2pi);
+  // scaling by 2^f and removing whole turns are then EXACT, and the remaining angle in [-pi, pi] goes to the
+  // SFU (abs error ~6e-7, independent of the frequency; libm sincosf costs ~8x the instructions)
 #pragma unroll
-  for (int f = F0; f <= F1; ++f) {
-    const float fr = (float)(1 << f);
+  for (int c = 0; c < 3; ++c) {
+    const float inv_hi = 0.15915494f, inv_lo = 6.4206382e-09f;
+    const float t_hi = __fmul_rn(p[c], inv_hi);
+    const float t_lo = __fmaf_rn(p[c], inv_lo, __fmaf_rn(p[c], inv_hi, -t_hi));
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sincosf(p[c] * fr, &sn[f - F0][c], &cs[f - F0][c]);
+    for (int f = F0; f <= F1; ++f) {
+      const float sc = (float)(1 << f);
+      const float a = t_hi * sc;                       // exact
+      const float turns = (a - rintf(a)) + t_lo * sc;  // fractional turns, |.| <= 0.5 (+ tiny)
+      const float ang = turns * 6.2831855f;
+      sn[f - F0][c] = __sinf(ang);
+      cs[f - F0][c] = __cosf(ang);
+    }
   }
 #pragma unroll
   for (int ch = CB; ch < CE; ++ch) {
@@ -405,11 +418,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   const int64_t n_utiles = (n_tiles + UT - 1) / UT;
 
   // ---- one-time setup --------------------------------------------------------------------
+  const int latent = args.latent_index + (args.latent_dev ? (int)__ldg(args.latent_dev) : 0);
   for (int i = threadIdx.x; i < BIAS_FLOATS; i += N_THREADS) {
     int l = i >> 8, j = i & 255;
     float b = 0.f;
     if (l < F.n_layers && j < F.layers[l].n_out) {
-      int t = min(max(args.latent_index, 0), F.layers[l].n_tables - 1);
+      int t = min(max(latent, 0), F.layers[l].n_tables - 1);
       b = F.bias[F.layers[l].bias_off + t * F.layers[l].n_out + j];
     }
     s_bias[i] = b;
@@ -647,12 +661,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               else write_pe<NPASS, 4, 2, 4>(a_hi, a_lo, PE_CHUNK0, row, vx, vy, vz);
             }
             // hidden layer: bias + ReLU -> bf16 (hi/lo) -> A chunks 8..39 in place; this thread: 128 of the 256 columns
+            // (hidden layers are 256 wide: 4 groups of 32 columns per thread), software-pipelined: the TMEM load of
+            // group g+1 is in flight while group g is converted and stored
             const bool alpha_layer = NERF && (l == F.n_layers - 2);
-            const int g0 = half * (n_pad / 64);
-            for (int g = g0; g < g0 + n_pad / 64; ++g) {
-              uint32_t v[32];
-              tmem_ld32(t_acc + g * 32, v);
-              tmem_ld_wait();
+            const int g0 = half * 4;
+            uint32_t va[32], vb[32];
+            auto process = [&](const uint32_t (&v)[32], int g) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float x[8];
@@ -663,27 +677,39 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
 #pragma unroll
                   for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[q * 8 + j]) + bb[j];
                   store_chunk<NPASS, NPASS == 1>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
-                  continue;
-                }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
-                if (alpha_layer) {
-                  const float4 w0 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8);
-                  const float4 w1 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8 + 4);
-                  float sg = sigma[t];
-                  sg = fmaf(x[0], w0.x, sg);
-                  sg = fmaf(x[1], w0.y, sg);
-                  sg = fmaf(x[2], w0.z, sg);
-                  sg = fmaf(x[3], w0.w, sg);
-                  sg = fmaf(x[4], w1.x, sg);
-                  sg = fmaf(x[5], w1.y, sg);
-                  sg = fmaf(x[6], w1.z, sg);
-                  sg = fmaf(x[7], w1.w, sg);
-                  sigma[t] = sg;
+                  for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
+                  if (alpha_layer) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(s_head + g * 32 + q * 8 + 4);
+                    float sg = sigma[t];
+                    sg = fmaf(x[0], w0.x, sg);
+                    sg = fmaf(x[1], w0.y, sg);
+                    sg = fmaf(x[2], w0.z, sg);
+                    sg = fmaf(x[3], w0.w, sg);
+                    sg = fmaf(x[4], w1.x, sg);
+                    sg = fmaf(x[5], w1.y, sg);
+                    sg = fmaf(x[6], w1.z, sg);
+                    sg = fmaf(x[7], w1.w, sg);
+                    sigma[t] = sg;
+                  }
+                  store_chunk<NPASS>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
                 }
-                store_chunk<NPASS>(a_hi, a_lo, HID_CHUNK0 + g * 4 + q, row, x);
               }
-            }
+            };
+            tmem_ld32(t_acc + g0 * 32, va);
+            tmem_ld_wait();
+            tmem_ld32(t_acc + (g0 + 1) * 32, vb);
+            process(va, g0);
+            tmem_ld_wait();
+            tmem_ld32(t_acc + (g0 + 2) * 32, va);
+            process(vb, g0 + 1);
+            tmem_ld_wait();
+            tmem_ld32(t_acc + (g0 + 3) * 32, vb);
+            process(va, g0 + 2);
+            tmem_ld_wait();
+            process(vb, g0 + 3);
             if (alpha_layer && half == 1) xchg[row * 4] = sigma[t];   // read by the row's other thread after the next acc barrier
             tc_fence_before();
             fence_proxy_async();
@@ -1011,7 +1037,7 @@ static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs 
 }
 
 // internal C++ entry points shared with render.cu
-int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *pts, const float *smpl_bw, const float *vol_w24,
+int bw_forward_impl(aninerf_net *net, int field, int latent_index, const int64_t *latent_dev, const float *pts, const float *smpl_bw, const float *vol_w24,
                     const int32_t dims[3], const float *bounds, int64_t n, const int32_t *n_dev, const float *A, float *bw_out,
                     float *tpts_out, int precision, cudaStream_t st) {
   MlpArgs a;
@@ -1019,6 +1045,7 @@ int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *
   int rc = fill_field(net, field, precision, a);
   if (rc) return rc;
   a.latent_index = latent_index;
+  a.latent_dev = latent_dev;
   a.pts = pts;
   a.n = n;
   a.n_dev = n_dev;
@@ -1034,7 +1061,7 @@ int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *
   return precision == 3 ? launch_mlp<3, false, 1>(a, st) : launch_mlp<1, false, 2>(a, st);
 }
 
-int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
+int nerf_forward_impl(aninerf_net *net, int latent_index, const int64_t *latent_dev, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
                       float *sigma_out, float *rgb_out, const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
                       float *sigma_masked_out, int precision, cudaStream_t st) {
   MlpArgs a;
@@ -1042,6 +1069,7 @@ int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, cons
   int rc = fill_field(net, ANINERF_FIELD_NERF, precision, a);
   if (rc) return rc;
   a.latent_index = latent_index;
+  a.latent_dev = latent_dev;
   a.pts = pts;
   a.viewdir = viewdir;
   a.n = n;
@@ -1129,7 +1157,7 @@ int aninerf_bw_forward(aninerf_net *net, int32_t field, int32_t latent_index, co
   ANI_CHECK_ARG(net && pts && smpl_bw && n >= 0 && (field == ANINERF_FIELD_BW || field == ANINERF_FIELD_NOVEL_BW));
   ANI_CHECK_ARG(!tpts_out || A);
   if (n == 0) return ANINERF_OK;
-  return bw_forward_impl(net, field, latent_index, pts, smpl_bw, nullptr, nullptr, nullptr, n, n_dev, A, bw_out, tpts_out, precision,
+  return bw_forward_impl(net, field, latent_index, nullptr, pts, smpl_bw, nullptr, nullptr, nullptr, n, n_dev, A, bw_out, tpts_out, precision,
                          (cudaStream_t)stream);
 }
 
@@ -1139,7 +1167,7 @@ int aninerf_nerf_forward(aninerf_net *net, int32_t latent_index, const float *pt
   ANI_CHECK_ARG(net && pts && viewdir && n >= 0);
   ANI_CHECK_ARG(!raw_out || (dists && tbounds && index));
   if (n == 0) return ANINERF_OK;
-  return nerf_forward_impl(net, latent_index, pts, viewdir, n, n_dev, sigma_out, rgb_out, dists, tbounds, index, raw_out, sigma_masked_out,
+  return nerf_forward_impl(net, latent_index, nullptr, pts, viewdir, n, n_dev, sigma_out, rgb_out, dists, tbounds, index, raw_out, sigma_masked_out,
                            precision, (cudaStream_t)stream);
 }
 

@@ -27,10 +27,10 @@ int launch_mask_points(const float *wpts, int64_t n, const float *R, const float
                        float *ppts, cudaStream_t st);
 int launch_gather_points(const float *src, const int32_t *index, const int32_t *count, int64_t cap, float *dst, cudaStream_t st);
 int launch_scatter_scalar(const float *src, const int32_t *index, const int32_t *count, int64_t cap, float *dst, cudaStream_t st);
-int bw_forward_impl(aninerf_net *net, int field, int latent_index, const float *pts, const float *smpl_bw, const float *vol_w24,
+int bw_forward_impl(aninerf_net *net, int field, int latent_index, const int64_t *latent_dev, const float *pts, const float *smpl_bw, const float *vol_w24,
                     const int32_t dims[3], const float *bounds, int64_t n, const int32_t *n_dev, const float *A, float *bw_out,
                     float *tpts_out, int precision, cudaStream_t st);
-int nerf_forward_impl(aninerf_net *net, int latent_index, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
+int nerf_forward_impl(aninerf_net *net, int latent_index, const int64_t *latent_dev, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
                       float *sigma_out, float *rgb_out, const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
                       float *sigma_masked_out, int precision, cudaStream_t st);
 
@@ -169,25 +169,28 @@ int aninerf_render_rays(aninerf_net *net, const aninerf_frame *fr, const aninerf
   }
   // 2. neural blend weights at the posed points + inverse LBS -> canonical points
   const int bw_field = pr->novel_pose ? ANINERF_FIELD_NOVEL_BW : ANINERF_FIELD_BW;
-  const int bw_latent = pr->novel_pose ? fr->bw_latent_index : fr->latent_index + 1;
+  // latent indices: host values, or (no host round trip) the batch's device int64 tensors + an offset
+  const int64_t *bw_lat_dev = pr->novel_pose ? fr->bw_latent_index_dev : fr->latent_index_dev;
+  const int bw_latent = pr->novel_pose ? (bw_lat_dev ? 0 : fr->bw_latent_index) : (bw_lat_dev ? 1 : fr->latent_index + 1);
+  const int nerf_latent = fr->latent_index_dev ? 0 : fr->latent_index;
   const int bw_prec = pr->bw_precision == 1 ? 1 : 3;
   {
     StageTimer t(ST_BW_POSE, st);
-    if ((rc = bw_forward_impl(net, bw_field, bw_latent, s.ppts, nullptr, s.w24_p, fr->pbw_dims, fr->pbounds, n, out->n_active, fr->A,
+    if ((rc = bw_forward_impl(net, bw_field, bw_latent, bw_lat_dev, s.ppts, nullptr, s.w24_p, fr->pbw_dims, fr->pbounds, n, out->n_active, fr->A,
                               pr->want_bw ? out->pbw_all : nullptr, s.tpts, bw_prec, st)))
       return rc;
   }
   // 3. (training contract only) blend weights of the canonical points, latent index 0
   if (pr->want_bw) {
     StageTimer t(ST_BW_CANON, st);
-    if ((rc = bw_forward_impl(net, ANINERF_FIELD_BW, 0, s.tpts, nullptr, s.w24_t, fr->tbw_dims, fr->tbounds, n, out->n_active, nullptr,
+    if ((rc = bw_forward_impl(net, ANINERF_FIELD_BW, 0, nullptr, s.tpts, nullptr, s.w24_t, fr->tbw_dims, fr->tbounds, n, out->n_active, nullptr,
                               out->tbw_all, nullptr, bw_prec, st)))
       return rc;
   }
   // 4. canonical NeRF field + tail of Network.forward, scattered into the dense raw buffer
   {
     StageTimer t(ST_NERF, st);
-    if ((rc = nerf_forward_impl(net, fr->latent_index, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds, index,
+    if ((rc = nerf_forward_impl(net, nerf_latent, fr->latent_index_dev, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds, index,
                                 out->raw, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st)))
       return rc;
   }
@@ -279,12 +282,13 @@ int aninerf_query_alpha(aninerf_net *net, const aninerf_frame *fr, const float *
     return rc;
   if ((rc = launch_gather_points(ppts_all, index, n_active, n, ppts, st))) return rc;
   const int bw_field = novel_pose ? ANINERF_FIELD_NOVEL_BW : ANINERF_FIELD_BW;
-  const int bw_latent = novel_pose ? fr->bw_latent_index : fr->latent_index + 1;
-  if ((rc = bw_forward_impl(net, bw_field, bw_latent, ppts, nullptr, w24, fr->pbw_dims, fr->pbounds, n, n_active, fr->A, nullptr, tpts,
+  const int64_t *bw_lat_dev = novel_pose ? fr->bw_latent_index_dev : fr->latent_index_dev;
+  const int bw_latent = novel_pose ? (bw_lat_dev ? 0 : fr->bw_latent_index) : (bw_lat_dev ? 1 : fr->latent_index + 1);
+  if ((rc = bw_forward_impl(net, bw_field, bw_latent, bw_lat_dev, ppts, nullptr, w24, fr->pbw_dims, fr->pbounds, n, n_active, fr->A, nullptr, tpts,
                             bw_precision == 1 ? 1 : 3, st)))
     return rc;
   // density only: the colour head is evaluated but discarded (viewdir = the canonical points, any finite input works)
-  if ((rc = nerf_forward_impl(net, fr->latent_index, tpts, tpts, n, n_active, sigma, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1,
+  if ((rc = nerf_forward_impl(net, fr->latent_index_dev ? 0 : fr->latent_index, fr->latent_index_dev, tpts, tpts, n, n_active, sigma, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1,
                               st)))
     return rc;
   ANI_CUDA(cudaMemsetAsync(sigma_out, 0, n * 4, st));

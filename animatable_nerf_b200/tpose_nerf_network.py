@@ -62,8 +62,16 @@ def _frame_struct(batch: dict, need_tbw: bool = True):
         tbw = dev('tbw')
         fr.tbw = tbw.data_ptr()
         fr.tbw_dims[:] = list(tbw.shape[-4:-1])
-    fr.latent_index = int(batch['latent_index'].reshape(-1)[0]) if 'latent_index' in batch else 0
-    fr.bw_latent_index = int(batch['bw_latent_index'].reshape(-1)[0]) if 'bw_latent_index' in batch else 0
+    for key in ('latent_index', 'bw_latent_index'):
+        if key not in batch:
+            continue
+        t = batch[key]
+        if torch.is_tensor(t) and t.is_cuda and t.dtype == torch.int64:
+            t = t.reshape(-1).contiguous()              # read by the kernels: no device->host sync per frame
+            keep[key] = t
+            setattr(fr, key + '_dev', t.data_ptr())
+        else:
+            setattr(fr, key, int(torch.as_tensor(t).reshape(-1)[0]))
     return fr, keep
 
 

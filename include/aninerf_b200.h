@@ -186,6 +186,11 @@ typedef struct {
   int32_t tbw_dims[3];
   int32_t latent_index;     /* batch['latent_index'] */
   int32_t bw_latent_index;  /* batch['bw_latent_index'] (novel pose) */
+  /* optional: the same two indices as DEVICE int64 scalars (how the reference batch holds them after
+   * .cuda()); when non-NULL they are read by the kernels and the host values above are ignored, so the
+   * host never waits on a device->host copy per frame */
+  const int64_t *latent_index_dev;
+  const int64_t *bw_latent_index_dev;
 } aninerf_frame;
 
 typedef struct {
