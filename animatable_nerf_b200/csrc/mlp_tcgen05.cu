@@ -373,7 +373,8 @@ struct Cfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM = FIXED + STAGES * STAGE_BYTES;
   static_assert(STAGES >= 2, "weight ring needs at least two stages");
-  static constexpr int TMEM_COLS = 256 * NT;
+  static constexpr int TMEM_COLS = 512;                         // NT = 2: one accumulator per slot; NT = 1: two, alternating by layer
+  static constexpr int N_AREADY = NT == 1 ? 4 : NT;             // NT = 1: one per 64-column quarter of the hidden layer (quarter pipelining)
   // offsets
   static constexpr int OFF_A_HI = 0;                            // slot t at t * A_BYTES
   static constexpr int OFF_A_LO = A_BYTES * NT;                 // only when NPASS == 3
@@ -399,12 +400,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
   const uint32_t bar_a_ready = smem_u32(bars + 2 * C::STAGES);
-  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + NT);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2 * NT);
-  static_assert((2 * C::STAGES + 2 * NT + 1) * 8 <= 192, "barrier block overflow");
+  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + C::N_AREADY);
+  // peer CTA only: its rows arrive here (cheap CTA-local arrives); one relay thread forwards each completed phase
+  // to the leader's a_ready with a single cluster-scope arrive
+  const uint32_t bar_a_local = smem_u32(bars + 2 * C::STAGES + C::N_AREADY + NT);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2 * C::N_AREADY + NT);
+  static_assert((2 * C::STAGES + 2 * C::N_AREADY + NT + 1) * 8 <= 216, "barrier block overflow");
+  // QP (NT == 1): the epilogue of layer l publishes the next layer's A operand quarter by quarter (a_ready[q]) and the
+  // accumulator alternates between two TMEM buffers, so the MMAs of layer l+1 start after the first quarter is written
+  constexpr bool QP = NT == 1;
   // last weight-stream position consumed from each ring stage: with one MMA thread per slot a thread only waits
   // on the `full` phases of its OWN steps, and a parity wait is only sound once the previous phase is known complete
-  volatile uint32_t *s_last = reinterpret_cast<volatile uint32_t *>(smem + C::OFF_BAR + 192);
+  volatile uint32_t *s_last = reinterpret_cast<volatile uint32_t *>(smem + C::OFF_BAR + 216);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR == 2 ? cluster_ctarank() : 0u;
@@ -439,10 +446,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       mbar_init(bar_full + 8 * s, (leader && PAIR == 2) ? 2 : 1);   // own bytes landed (+ the peer's relay on the leader)
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int t = 0; t < NT; ++t) {
-      mbar_init(bar_a_ready + 8 * t, ROW_THREADS * PAIR);
-      mbar_init(bar_acc + 8 * t, 1);
+    for (int t = 0; t < C::N_AREADY; ++t) {
+      mbar_init(bar_a_ready + 8 * t, ROW_THREADS + (PAIR == 2 ? 1 : 0));   // the leader's rows + the peer's relay
+      mbar_init(bar_a_local + 8 * t, ROW_THREADS);
     }
+    for (int t = 0; t < NT; ++t) mbar_init(bar_acc + 8 * t, 1);
     for (int s = 0; s < C::STAGES; ++s) s_last[s] = 0xffffffffu;
     fence_barrier_init();
   }
@@ -487,7 +495,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       const uint32_t a_lbo = (uint32_t)CHUNK_BYTES, a_sbo = 128u;   // K-direction / 8-row-group strides
       const int t = my_slot;
       const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI + t * A_BYTES), a_lo = smem_u32(smem + C::OFF_A_LO + t * A_BYTES);
-      const uint32_t acc = tmem_base + (uint32_t)(t * 256);
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
         const bool tracing = args.trace && blockIdx.x == 0 && ut == 0 && lane == 0;
         for (int l = 0; l < F.n_layers; ++l) {
@@ -497,12 +504,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           const uint32_t b_k_stride = (uint32_t)(n_pad / PAIR) * 16u;   // bytes between K core matrices (this CTA's rows)
           const uint32_t b_lbo = b_k_stride, b_sbo = 128u;
           g += (uint32_t)(t * n_layer_steps);                           // the earlier slots' copies of this layer
+          const uint32_t acc = tmem_base + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
           ANI_TRACE(8 + 16 * l + 8 * t + 4);
-          mbar_wait<PAIR == 2>(bar_a_ready + 8 * t, a_phase, 2 + 10 * t);   // every row of the slot wrote its A operand, accumulator drained
-          a_phase ^= 1;
+          // the A operand is ready (QP: its first quarter) and the accumulator has been drained
+          int next_q = 1;
+          mbar_wait<PAIR == 2>(bar_a_ready + 8 * (QP ? 0 : t), a_phase, 2 + 10 * t);
           ANI_TRACE(8 + 16 * l + 8 * t + 5);
           for (int s = s0; s < s0 + n_layer_steps; ++s, ++g) {
             const Step st = s_steps[s];
+            if (QP && st.a_chunk >= HID_CHUNK0) {
+              const int q_last = (st.a_chunk - HID_CHUNK0 + 2 * st.n_k16 - 1) >> 3;   // hidden chunk c belongs to quarter c / 8
+              for (; next_q <= q_last; ++next_q) mbar_wait<PAIR == 2>(bar_a_ready + 8 * next_q, a_phase, 6);
+            }
             const uint32_t stage = g % C::STAGES, phase = (g / C::STAGES) & 1u;
             if (NT > 1 && g >= (uint32_t)C::STAGES) {
               // the previous use of this stage (possibly the other slot's) must have been consumed first
@@ -539,7 +552,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             __syncwarp();
           }
           ANI_TRACE(8 + 16 * l + 8 * t + 6);
+          if (QP)
+            for (; next_q < 4; ++next_q) mbar_wait<PAIR == 2>(bar_a_ready + 8 * next_q, a_phase, 7);   // keep every quarter's phase in step
+          a_phase ^= 1;
           g += (uint32_t)((NT - 1 - t) * n_layer_steps);      // the later slots' copies of this layer
+        }
+      }
+    } else if (lane == 0 && PAIR == 2 && !leader && my_slot == 1) {
+      // ===== relay (peer CTA): forward "this CTA's rows have written their A operand" to the leader =====
+      const uint32_t a_ready_leader = mapa_u32(bar_a_ready, 0);
+      uint32_t ph = 0;
+      for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+        for (int l = 0; l < F.n_layers; ++l) {
+          for (int b = 0; b < C::N_AREADY; ++b) {
+            mbar_wait(bar_a_local + 8 * b, ph, 8);
+            mbar_arrive_cluster(a_ready_leader + 8 * b);
+          }
+          ph ^= 1;
         }
       }
     } else if (lane == 0 && PAIR == 2 && !leader && my_slot == 0) {
@@ -563,7 +592,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     const int row = (warp & 3) * 32 + lane;            // == TMEM lane; warps w and w+4 share a row
     const int half = warp >> 2;                        // which half of the columns this thread owns
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t a_ready_leader = PAIR == 2 ? mapa_u32(bar_a_ready, 0) : bar_a_ready;
+    const uint32_t a_arrive = leader ? bar_a_ready : bar_a_local;   // rows always arrive CTA-locally
     uint32_t acc_phase = 0;
     for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
       const bool tracing = args.trace && blockIdx.x == 0 && ut == 0 && threadIdx.x == 0;
@@ -586,8 +615,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         if (half == 0) write_pe<NPASS, 10, 0, 4>(a_hi, a_lo, PE_CHUNK0, row, px[t], py[t], pz[t]);
         else write_pe<NPASS, 10, 4, 8>(a_hi, a_lo, PE_CHUNK0, row, px[t], py[t], pz[t]);
         fence_proxy_async();
-        if (leader) mbar_arrive(bar_a_ready + 8 * t);
-        else mbar_arrive_cluster(a_ready_leader + 8 * t);
+#pragma unroll
+        for (int q = 0; q < (QP ? 4 : 1); ++q) {       // QP: the input encoding readies every quarter's barrier for layer 0
+          const int bi = QP ? q : t;
+          mbar_arrive(a_arrive + 8 * bi);
+        }
       }
       ANI_TRACE(1);
 
@@ -599,7 +631,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         for (int t = 0; t < NT; ++t) {
           uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
           float *xchg = s_xchg + t * (TILE_M * 4);           // this slot's exchange between the row's two threads
-          const uint32_t t_acc = t_lane + (uint32_t)(t * 256);
+          const uint32_t t_acc = t_lane + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
           float smpl[ANINERF_N_BONES];
           if (!NERF && last && half == 0) {
             // initial SMPL weights of this row, fetched while the last layer's MMAs run
@@ -664,7 +696,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             // (hidden layers are 256 wide: 4 groups of 32 columns per thread), software-pipelined: the TMEM load of
             // group g+1 is in flight while group g is converted and stored
             const bool alpha_layer = NERF && (l == F.n_layers - 2);
-            const int g0 = half * 4;
             uint32_t va[32], vb[32];
             auto process = [&](const uint32_t (&v)[32], int g) {
 #pragma unroll
@@ -698,23 +729,31 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                 }
               }
             };
-            tmem_ld32(t_acc + g0 * 32, va);
+            // publish the columns written so far (QP: after every group = one quarter of the next layer's K)
+            auto publish = [&](int q) {
+              tc_fence_before();
+              fence_proxy_async();
+              mbar_arrive(a_arrive + 8 * q);
+            };
+            // this thread's i-th group of 32 columns: QP interleaves the row's two threads inside every quarter
+            const int ga = QP ? half : half * 4, gs = QP ? 2 : 1;
+            tmem_ld32(t_acc + ga * 32, va);
             tmem_ld_wait();
-            tmem_ld32(t_acc + (g0 + 1) * 32, vb);
-            process(va, g0);
+            tmem_ld32(t_acc + (ga + gs) * 32, vb);
+            process(va, ga);
+            if (QP) publish(0);
             tmem_ld_wait();
-            tmem_ld32(t_acc + (g0 + 2) * 32, va);
-            process(vb, g0 + 1);
+            tmem_ld32(t_acc + (ga + 2 * gs) * 32, va);
+            process(vb, ga + gs);
+            if (QP) publish(1);
             tmem_ld_wait();
-            tmem_ld32(t_acc + (g0 + 3) * 32, vb);
-            process(va, g0 + 2);
+            tmem_ld32(t_acc + (ga + 3 * gs) * 32, vb);
+            process(va, ga + 2 * gs);
+            if (QP) publish(2);
             tmem_ld_wait();
-            process(vb, g0 + 3);
+            process(vb, ga + 3 * gs);
             if (alpha_layer && half == 1) xchg[row * 4] = sigma[t];   // read by the row's other thread after the next acc barrier
-            tc_fence_before();
-            fence_proxy_async();
-            if (leader) mbar_arrive(bar_a_ready + 8 * t);
-            else mbar_arrive_cluster(a_ready_leader + 8 * t);
+            publish(QP ? 3 : t);
             ANI_TRACE(8 + 16 * l + 8 * t + 2);
           } else if (!NERF) {
             // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
