@@ -51,6 +51,10 @@ class RenderOutputs(C.Structure):
                 ('n_active', C.c_void_p), ('chunk_offsets', C.c_void_p)]
 
 
+class Silhouettes(C.Structure):
+    _fields_ = [('msks', C.c_void_p), ('Ks', C.c_void_p), ('RT', C.c_void_p), ('n_views', C.c_int32), ('H', C.c_int32), ('W', C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/aninerf_b200.h declares
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 PROTOTYPES = {
@@ -78,6 +82,9 @@ PROTOTYPES = {
     'aninerf_render_workspace_bytes': (_I64, [_I64, _I32, _I32, _I64, _I64]),
     'aninerf_render_rays': (_I32, [_VP, C.POINTER(Frame), C.POINTER(RenderParams), _VP, _VP, _VP, _VP, _VP, _VP, _I64,
                                    C.POINTER(RenderOutputs), _VP, _I64, _VP]),
+    'aninerf_render_rays_culled': (_I32, [_VP, C.POINTER(Frame), C.POINTER(RenderParams), C.POINTER(Silhouettes), _VP, _VP, _VP, _VP, _VP,
+                                          _VP, _I64, C.POINTER(RenderOutputs), _VP, _I64, _VP]),
+    'aninerf_inside_all_views': (_I32, [_VP, _I64, C.POINTER(Silhouettes), _VP, _VP]),
     'aninerf_query_workspace_bytes': (_I64, [_I64, _I64]),
     'aninerf_query_alpha': (_I32, [_VP, C.POINTER(Frame), _VP, _I64, _I64, _F, _I32, _I32, _VP, _VP, _VP, _I64, _VP]),
 }

@@ -422,6 +422,69 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
 // =============================================================================================
 constexpr int MB = 2048;   // samples per mask block (8 per thread, 256 threads)
 
+// ---- multi-view silhouette culling (prepare_inside_pts, tpose_renderer_mmsk.py:14-57) ----------
+// A world point survives when it projects into the (dilated) body mask of EVERY training view:
+//   cam = pts @ R^T + T ; img = cam @ K^T ; uv = round(img.xy / img.z) clamped to the image ; msk[v,u] != 0
+// torch.matmul((1,m,3),(1,3,3)^T) on the CPU is bit-equal to the FMA chain below (checked in
+// tests/test_oracle_golden.py); round() is round-half-to-even (rintf); the rest is integer work.
+constexpr int SIL_MAX_STAGED = 32;   // views whose K / RT are staged in shared memory
+struct SilDev {
+  const uint8_t *msks;   // (V,H,W)
+  const float *Ks;       // (V,3,3)
+  const float *RT;       // (V,4,4)
+  int V, H, W;
+};
+struct SilShared {
+  float K[SIL_MAX_STAGED][9];
+  float RT[SIL_MAX_STAGED][12];
+};
+
+__device__ __forceinline__ void stage_silhouettes(const SilDev &s, SilShared *sh) {
+  if (!s.msks) return;
+  const int V = min(s.V, SIL_MAX_STAGED);
+  for (int i = threadIdx.x; i < V * 9; i += blockDim.x) sh->K[i / 9][i % 9] = s.Ks[i];
+  for (int i = threadIdx.x; i < V * 12; i += blockDim.x) sh->RT[i / 12][i % 12] = s.RT[(i / 12) * 16 + i % 12];
+}
+
+__device__ __forceinline__ bool inside_view(const float *K, const float *RT, const uint8_t *msk, int H, int W, float x, float y, float z) {
+  float c[3], q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    c[i] = __fadd_rn(__fmaf_rn(z, RT[4 * i + 2], __fmaf_rn(y, RT[4 * i + 1], __fmul_rn(x, RT[4 * i]))), RT[4 * i + 3]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) q[i] = __fmaf_rn(c[2], K[3 * i + 2], __fmaf_rn(c[1], K[3 * i + 1], __fmul_rn(c[0], K[3 * i])));
+  long long u = __float2ll_rn(__fdiv_rn(q[0], q[2]));   // .round().long(): half-to-even, then the integer cast
+  long long v = __float2ll_rn(__fdiv_rn(q[1], q[2]));
+  u = u < 0 ? 0 : (u > W - 1 ? W - 1 : u);
+  v = v < 0 ? 0 : (v > H - 1 ? H - 1 : v);
+  return __ldg(msk + v * W + u) != 0;
+}
+
+__device__ __forceinline__ bool inside_all_views(const SilDev &s, const SilShared *sh, float x, float y, float z) {
+  const int64_t plane = (int64_t)s.H * s.W;
+  for (int v = 0; v < s.V; ++v) {
+    bool in = v < SIL_MAX_STAGED ? inside_view(sh->K[v], sh->RT[v], s.msks + v * plane, s.H, s.W, x, y, z)
+                                 : false;
+    if (v >= SIL_MAX_STAGED) {   // beyond the staged set: read the matrices from global memory
+      float K[9], RT[12];
+      for (int i = 0; i < 9; ++i) K[i] = __ldg(s.Ks + v * 9 + i);
+      for (int i = 0; i < 12; ++i) RT[i] = __ldg(s.RT + v * 16 + i);
+      in = inside_view(K, RT, s.msks + v * plane, s.H, s.W, x, y, z);
+    }
+    if (!in) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) inside_kernel(const float *__restrict__ wpts, int64_t n, SilDev s, uint8_t *__restrict__ inside) {
+  __shared__ SilShared sh;
+  stage_silhouettes(s, &sh);
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  inside[i] = inside_all_views(s, &sh, wpts[3 * i], wpts[3 * i + 1], wpts[3 * i + 2]) ? 1 : 0;
+}
+
 struct SampleSetup {
   const float *ray_o, *ray_d, *near, *far, *t_vals, *t_rand;
   int64_t n_rays;
@@ -429,6 +492,7 @@ struct SampleSetup {
   const float *R, *Th, *bounds;   // device: (3,3), (3,), (2,3) -- no host round trip per frame
   int dim[3];
   float norm_th;
+  SilDev sil;                     // sil.msks == nullptr: no silhouette culling
 };
 
 // stage the per-frame rigid transform and volume grid in shared memory (call before __syncthreads)
@@ -472,7 +536,9 @@ __global__ void __launch_bounds__(256) mask_kernel(SampleSetup p, const float *_
   __shared__ unsigned long long s_min[8];
   __shared__ RigidFrame s_frame;
   __shared__ VolumeGrid s_grid;
+  __shared__ SilShared s_sil;
   stage_frame(p.R, p.Th, p.bounds, p.dim, &s_frame, &s_grid);
+  stage_silhouettes(p.sil, &s_sil);
   if (threadIdx.x < p.S) {
     float t = p.t_vals[threadIdx.x];
     st[threadIdx.x] = t;
@@ -495,17 +561,21 @@ __global__ void __launch_bounds__(256) mask_kernel(SampleSetup p, const float *_
       const int s = (int)(i & (uint32_t)(p.S - 1));
       float z, wx, wy, wz, px, py, pz;
       sample_at(p, st, s1mt, r, s, z, wx, wy, wz);
-      world_to_pose(s_frame, wx, wy, wz, px, py, pz);
-      float w[8];
-      int off[8];
-      trilinear_corners(s_grid, px, py, pz, w, off);
-      float pn = 0.f;
+      // tpose_renderer_mmsk.py:71-90: only samples inside every training-view silhouette reach the network
+      // (and are candidates of its per-chunk argmin forcing)
+      if (!p.sil.msks || inside_all_views(p.sil, &s_sil, wx, wy, wz)) {
+        world_to_pose(s_frame, wx, wy, wz, px, py, pz);
+        float w[8];
+        int off[8];
+        trilinear_corners(s_grid, px, py, pz, w, off);
+        float pn = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (off[k] >= 0) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
-      act = pn < p.norm_th;
-      unsigned long long key = ((unsigned long long)float_key(pn) << 32) | (unsigned long long)(chunk_base + it * 256 + threadIdx.x);
-      best = key < best ? key : best;
+        for (int k = 0; k < 8; ++k)
+          if (off[k] >= 0) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
+        act = pn < p.norm_th;
+        unsigned long long key = ((unsigned long long)float_key(pn) << 32) | (unsigned long long)(chunk_base + it * 256 + threadIdx.x);
+        best = key < best ? key : best;
+      }
     }
     unsigned bal = __ballot_sync(0xffffffffu, act);
     if (lane == 0) {
@@ -544,7 +614,7 @@ __global__ void force_argmin_kernel(int64_t n_chunks, int64_t blocks_per_chunk, 
   int64_t b0 = c * blocks_per_chunk, b1 = min(n_blocks, b0 + blocks_per_chunk);
   int tot = 0;
   for (int64_t b = b0; b < b1; ++b) tot += block_counts[b];
-  if (tot == 0) {
+  if (tot == 0 && chunk_argmin[c] != ~0ull) {   // ~0: silhouette culling left the chunk empty, the network is not called
     int64_t local = (int64_t)(chunk_argmin[c] & 0xffffffffull);
     int64_t i = c * chunk_samples + local;
     mask_words[i / 32] |= 1u << (i % 32);
@@ -814,6 +884,16 @@ int aninerf_sample_blend_weights(const float *pts, int64_t n, const float *vol, 
   return ANINERF_OK;
 }
 
+int aninerf_inside_all_views(const float *wpts, int64_t n, const aninerf_silhouettes *sil, uint8_t *inside, void *stream) {
+  ANI_CHECK_ARG(wpts && sil && inside && n >= 0);
+  ANI_CHECK_ARG(sil->msks && sil->Ks && sil->RT && sil->n_views > 0 && sil->H > 0 && sil->W > 0);
+  if (n == 0) return ANINERF_OK;
+  SilDev s{sil->msks, sil->Ks, sil->RT, sil->n_views, sil->H, sil->W};
+  inside_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wpts, n, s, inside);
+  ANI_LAUNCHED();
+  return ANINERF_OK;
+}
+
 int aninerf_inverse_lbs(const float *ppts, const float *bw, int64_t n, const float *A, float *tpts, void *stream) {
   ANI_CHECK_ARG(ppts && bw && A && tpts && n >= 0);
   if (n == 0) return ANINERF_OK;
@@ -872,8 +952,10 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
                      const float *t_rand, int64_t n_rays, int S, int chunk_rays, const float *R, const float *Th,
                      const float *bounds, const int32_t dims[3], const float *dist_plane, float norm_th, FrontEndBuffers fb,
                      int32_t *index, float *ppts, float *viewdir, float *dists, int32_t *n_active, int32_t *chunk_offsets,
-                     cudaStream_t st) {
+                     const aninerf_silhouettes *sil, cudaStream_t st) {
   SampleSetup p;
+  p.sil = SilDev{nullptr, nullptr, nullptr, 0, 0, 0};
+  if (sil) p.sil = SilDev{sil->msks, sil->Ks, sil->RT, sil->n_views, sil->H, sil->W};
   p.ray_o = ray_o; p.ray_d = ray_d; p.near = near; p.far = far; p.t_vals = t_vals; p.t_rand = t_rand;
   p.n_rays = n_rays; p.S = S; p.norm_th = norm_th;
   p.R = R; p.Th = Th; p.bounds = bounds;

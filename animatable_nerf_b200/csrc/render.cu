@@ -19,7 +19,7 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
                      const float *t_rand, int64_t n_rays, int S, int chunk_rays, const float *R, const float *Th,
                      const float *bounds, const int32_t dims[3], const float *dist_plane, float norm_th, FrontEndBuffers fb,
                      int32_t *index, float *ppts, float *viewdir, float *dists, int32_t *n_active, int32_t *chunk_offsets,
-                     cudaStream_t st);
+                     const aninerf_silhouettes *sil, cudaStream_t st);
 int launch_composite_fused(const float *raw, const float *near, const float *far, const float *t_vals, const float *z_vals, int64_t n_rays,
                            int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, cudaStream_t st);
 int launch_mask_points(const float *wpts, int64_t n, const float *R, const float *Th, const float *bounds, const int32_t dims[3],
@@ -117,6 +117,11 @@ static int64_t carve_render(Carver &c, int64_t n_rays, int S, int want_bw, int64
 
 using namespace aninerf;
 
+static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
+                            const float *ray_o, const float *ray_d, const float *near, const float *far, const float *t_vals,
+                            const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
+                            int64_t workspace_bytes, void *stream);
+
 extern "C" {
 
 int64_t aninerf_render_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_t want_bw, int64_t pbw_voxels, int64_t tbw_voxels) {
@@ -128,6 +133,24 @@ int64_t aninerf_render_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_
 int aninerf_render_rays(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const float *ray_o, const float *ray_d,
                         const float *near, const float *far, const float *t_vals, const float *t_rand, int64_t n_rays,
                         const aninerf_render_outputs *out, void *workspace, int64_t workspace_bytes, void *stream) {
+  return render_rays_impl(net, fr, pr, nullptr, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
+}
+
+int aninerf_render_rays_culled(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
+                               const float *ray_o, const float *ray_d, const float *near, const float *far, const float *t_vals,
+                               const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
+                               int64_t workspace_bytes, void *stream) {
+  ANI_CHECK_ARG(sil && sil->msks && sil->Ks && sil->RT && sil->n_views > 0 && sil->H > 0 && sil->W > 0);
+  ANI_CHECK_ARG(pr && !pr->want_bw);
+  return render_rays_impl(net, fr, pr, sil, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
+                            const float *ray_o, const float *ray_d, const float *near, const float *far, const float *t_vals,
+                            const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
+                            int64_t workspace_bytes, void *stream) {
   ANI_CHECK_ARG(net && fr && pr && out && ray_o && ray_d && near && far && t_vals && workspace && n_rays >= 0);
   ANI_CHECK_ARG(fr->A && fr->R && fr->Th && fr->pbw && fr->pbounds && fr->tbounds);
   ANI_CHECK_ARG(out->rgb_map && out->acc_map && out->depth_map && out->raw && out->n_active);
@@ -164,7 +187,7 @@ int aninerf_render_rays(aninerf_net *net, const aninerf_frame *fr, const aninerf
   {
     StageTimer t(ST_MASK, st);
     if ((rc = launch_front_end(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, pr->chunk_rays, fr->R, fr->Th, fr->pbounds, fr->pbw_dims,
-                               s.dist_p, pr->norm_th, s.fb, index, s.ppts, s.viewdir, s.dists, out->n_active, out->chunk_offsets, st)))
+                               s.dist_p, pr->norm_th, s.fb, index, s.ppts, s.viewdir, s.dists, out->n_active, out->chunk_offsets, sil, st)))
       return rc;
   }
   // 2. neural blend weights at the posed points + inverse LBS -> canonical points
@@ -203,6 +226,8 @@ int aninerf_render_rays(aninerf_net *net, const aninerf_frame *fr, const aninerf
   }
   return launch_composite_fused(out->raw, near, far, t_vals, z, n_rays, S, pr->white_bkgd, out->rgb_map, out->acc_map, out->depth_map, st);
 }
+
+extern "C" {
 
 int aninerf_profile_enable(int32_t on) {
   g_profile = on != 0;

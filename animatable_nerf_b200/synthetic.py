@@ -182,3 +182,45 @@ def make_state_dict(seed: int = 0, num_train_frame: int = 60, num_eval_frame: in
 def make_rays(frame: dict, H: int = 1024, W: int = 1024, focal: float = 1070.0, distance: float = 3.0, azimuth: float = 0.0):
     """Host-side (numpy restatement free) camera for a frame: returns K, R, T for the GPU front end."""
     return make_camera(frame, H, W, focal, distance, azimuth)
+
+
+# ---------------------------------------------------------------------------------------------
+# training-view silhouettes for the novel-view renderer (tpose_renderer_mmsk)
+# ---------------------------------------------------------------------------------------------
+def make_silhouettes(frame: dict, n_views: int = 4, H: int = 256, W: int = 256, focal: float = 270.0, distance: float = 3.0,
+                     radius: int = 6):
+    """`msks (V,H,W) u8`, `Ks (V,3,3) f32`, `RT (V,4,4) f32` as lib/datasets/tpose_novel_view_dataset.py:123-194
+    prepares them: per training view the body silhouette, dilated (the reference dilates the mask the same way).
+    Here the silhouette is the union of discs of `radius` pixels around the projected posed vertices."""
+    v = frame['wverts'].astype(np.float64)
+    msks = np.zeros((n_views, H, W), dtype=np.uint8)
+    Ks = np.zeros((n_views, 3, 3), dtype=np.float32)
+    RT = np.zeros((n_views, 4, 4), dtype=np.float32)
+    yy, xx = np.mgrid[-radius:radius + 1, -radius:radius + 1]
+    disc = (yy * yy + xx * xx) <= radius * radius
+    for i in range(n_views):
+        K, R, T = make_camera(frame, H, W, focal=focal, distance=distance, azimuth=2 * np.pi * i / n_views)
+        cam = v @ R.T + T.ravel()
+        uv = cam @ K.T
+        uv = np.rint(uv[:, :2] / uv[:, 2:]).astype(int)
+        m = np.zeros((H + 2 * radius, W + 2 * radius), dtype=bool)
+        ok = (uv[:, 0] >= 0) & (uv[:, 0] < W) & (uv[:, 1] >= 0) & (uv[:, 1] < H)
+        for x, y in uv[ok]:
+            m[y:y + 2 * radius + 1, x:x + 2 * radius + 1] |= disc
+        msks[i] = m[radius:radius + H, radius:radius + W]
+        Ks[i] = K.astype(np.float32)
+        RT[i, :3, :3] = R.astype(np.float32)
+        RT[i, :3, 3] = T.ravel().astype(np.float32)
+        RT[i, 3, 3] = 1
+    return msks, Ks, RT
+
+
+def add_silhouettes(batch: dict, frame: dict, device='cpu', **kw) -> dict:
+    msks, Ks, RT = make_silhouettes(frame, **kw)
+    b = dict(batch)
+    b['msks'] = torch.from_numpy(msks)[None].to(device)
+    b['Ks'] = torch.from_numpy(Ks)[None].to(device)
+    b['RT'] = torch.from_numpy(RT)[None].to(device)
+    b['H'] = torch.tensor([msks.shape[1]])
+    b['W'] = torch.tensor([msks.shape[2]])
+    return b

@@ -105,6 +105,23 @@ int aninerf_inverse_lbs(const float *ppts, const float *bw, int64_t n, const flo
 int aninerf_forward_lbs(const float *tpts, const float *bw, int64_t n, const float *A, float *ppts, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-view silhouette culling, Renderer.prepare_inside_pts,
+ * lib/networks/renderer/tpose_renderer_mmsk.py:14-57 (batch keys `msks`, `Ks`, `RT`, `H`, `W` of
+ * lib/datasets/tpose_novel_view_dataset.py:191)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint8_t *msks;  /* (V,H,W) uint8, dilated training-view body masks */
+  const float *Ks;      /* (V,3,3) intrinsics */
+  const float *RT;      /* (V,4,4) world->camera */
+  int32_t n_views, H, W;
+} aninerf_silhouettes;
+
+/* inside[i] = 1 iff world point i projects (round-half-even, clamped to the image) onto a non-zero
+ * mask pixel in EVERY view.  Bit-exact against the reference's CPU path. */
+int aninerf_inside_all_views(const float *wpts, int64_t n, const aninerf_silhouettes *sil_host, uint8_t *inside,
+                             void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage 5: alpha compositing, raw2outputs, lib/networks/renderer/nerf_net_utils.py:6-36
  * ---------------------------------------------------------------------------------------- */
 /* raw: (n_rays,S,4) = (r,g,b,alpha) already activated; z_vals: (n_rays,S).
@@ -228,6 +245,16 @@ int aninerf_render_rays(aninerf_net *net, const aninerf_frame *frame_host, const
                         const float *t_vals, const float *t_rand, int64_t n_rays,
                         const aninerf_render_outputs *out_host, void *workspace, int64_t workspace_bytes,
                         void *stream);
+
+/* tpose_renderer_mmsk.Renderer.render (tpose_renderer_mmsk.py:99-166): the same frame render with the
+ * samples culled by the training-view silhouettes BEFORE the network (so the per-chunk argmin forcing
+ * of Network.forward runs over the survivors only, and a chunk without survivors evaluates nothing).
+ * out_host->raw is still required (compositing input); want_bw must be 0 (the reference returns maps only). */
+int aninerf_render_rays_culled(aninerf_net *net, const aninerf_frame *frame_host, const aninerf_render_params *params_host,
+                               const aninerf_silhouettes *sil_host, const float *ray_o, const float *ray_d, const float *near,
+                               const float *far, const float *t_vals, const float *t_rand, int64_t n_rays,
+                               const aninerf_render_outputs *out_host, void *workspace, int64_t workspace_bytes,
+                               void *stream);
 
 /* Network.calculate_alpha (= get_alpha), tpose_nerf_network.py:105-137: density-only query of
  * world points (norm_th hard-coded 0.1 by the reference -- passed in), processed in chunks of

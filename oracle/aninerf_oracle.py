@@ -383,3 +383,60 @@ def render(sd, batch, cfg=None, t_rand=None, return_debug=False):
         dbg['chunk_active'] = torch.tensor([int(r['_debug']['pind'].sum()) for r in outs])
         out['_debug'] = dbg
     return out
+
+
+# ----------------------------------------------------------------------------
+# novel-view / pose-sequence renderer with multi-view silhouette culling
+# -- lib/networks/renderer/tpose_renderer_mmsk.py:14-166
+# ----------------------------------------------------------------------------
+def inside_all_views(pts, batch):
+    """prepare_inside_pts, tpose_renderer_mmsk.py:14-57.  pts (1,m,3) -> bool (1,m): the sample projects
+    into the (dilated) silhouette of EVERY training view."""
+    H, W = int(batch['H']), int(batch['W'])
+    inside = None
+    for nv in range(batch['Ks'].size(1)):
+        R = batch['RT'][:, nv, :3, :3]
+        T = batch['RT'][:, nv, :3, 3]
+        p = torch.matmul(pts, R.transpose(2, 1)) + T[:, None]
+        p = torch.matmul(p, batch['Ks'][:, nv].transpose(2, 1))
+        xy = (p[..., :2] / p[..., 2:]).round().long()
+        xy[..., 0] = torch.clamp(xy[..., 0], 0, W - 1)
+        xy[..., 1] = torch.clamp(xy[..., 1], 0, H - 1)
+        xy = xy[0]
+        m = batch['msks'][0, nv][xy[:, 1], xy[:, 0]][None].bool()
+        inside = m if inside is None else inside * m
+    return inside
+
+
+def render_mmsk(sd, batch, cfg=None, return_debug=False):
+    """tpose_renderer_mmsk.Renderer.render: per 2048-ray chunk, cull samples outside any training-view
+    silhouette, run Network.forward on the survivors only, composite.  Returns rgb/acc/depth maps."""
+    cfg = cfg or OracleCfg()
+    ray_o, ray_d, near, far = batch['ray_o'], batch['ray_d'], batch['near'], batch['far']
+    R = ray_o.shape[1]
+    S = cfg.N_samples
+    outs, dbg_inside, dbg_active = [], [], []
+    with torch.no_grad():
+        for i in range(0, R, cfg.chunk):
+            o, d = ray_o[:, i:i + cfg.chunk], ray_d[:, i:i + cfg.chunk]
+            pts, z = sample_points(o, d, near[:, i:i + cfg.chunk], far[:, i:i + cfg.chunk], S)
+            nb, npix = pts.shape[:2]
+            inside = inside_all_views(pts.view(nb, -1, 3), batch).view(-1)
+            full_raw = torch.zeros([nb * npix * S, 4])
+            n_act = 0
+            if inside.sum() > 0:
+                w = pts.view(-1, 3)[inside]
+                view = d[:, :, None].repeat(1, 1, S, 1).contiguous().view(-1, 3)[inside]
+                dist = sample_dists(z).view(-1)[inside]
+                ret = network_forward(sd, w, view, dist, batch, cfg, return_debug=True)
+                full_raw[inside] = ret['raw'][0]
+                n_act = int(ret['_debug']['pind'].sum())
+            raw = full_raw.reshape(-1, S, 4)
+            rgb_map, disp, acc, wgt, depth = raw2outputs(raw, z.view(-1, S), cfg.white_bkgd)
+            outs.append({'rgb_map': rgb_map.view(nb, npix, -1), 'acc_map': acc.view(nb, npix), 'depth_map': depth.view(nb, npix)})
+            dbg_inside.append(inside)
+            dbg_active.append(n_act)
+    out = {k: torch.cat([r[k] for r in outs], dim=1) for k in outs[0]}
+    if return_debug:
+        out['_debug'] = {'inside': torch.cat(dbg_inside), 'chunk_active': torch.tensor(dbg_active)}
+    return out

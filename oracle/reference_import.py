@@ -74,6 +74,7 @@ def load(cfg_file='configs/aninerf_313.yaml', overrides=()):
         from lib.networks.renderer import nerf_net_utils
         from lib.utils import blend_utils
         from lib.networks import embedder
+        from lib.networks.renderer import tpose_renderer_mmsk as mmsk_mod
     finally:
         sys.argv = saved_argv
         os.chdir(saved_cwd)
@@ -83,5 +84,5 @@ def load(cfg_file='configs/aninerf_313.yaml', overrides=()):
             os.environ['CUDA_VISIBLE_DEVICES'] = saved_cvd
     _loaded = types.SimpleNamespace(cfg=cfg, Network=net_mod.Network, Renderer=ren_mod.Renderer,
                                     net_mod=net_mod, dutils=dutils, nerf_net_utils=nerf_net_utils,
-                                    blend_utils=blend_utils, embedder=embedder)
+                                    blend_utils=blend_utils, embedder=embedder, MmskRenderer=mmsk_mod.Renderer)
     return _loaded

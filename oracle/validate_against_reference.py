@@ -168,6 +168,24 @@ def main():
                         alpha_grid=ga_r.numpy(), jitter_t_rand=t_rand.numpy(),
                         **{'jitter_' + k: out_rj[k].numpy() for k in ('rgb_map', 'acc_map', 'depth_map')})
 
+    # ---------------- silhouette-culled renderer (tpose_renderer_mmsk) --------------------------
+    mb = synthetic.add_silhouettes(batch, small, n_views=4)
+    with torch.no_grad():
+        mren = ref.MmskRenderer(net)
+        ins_r = mren.prepare_inside_pts(pts_r[:, :2048], mb)
+        ins_o = O.inside_all_views(pts_r[:, :2048].reshape(1, -1, 3), mb)
+        report('Renderer.prepare_inside_pts (4 views)', 'tpose_renderer_mmsk.py:14-57', biteq(ins_r.numpy(), ins_o.numpy()),
+               f'bit-equal; {int(ins_r.sum())} of {ins_r.numel()} samples inside every silhouette')
+        out_rm = mren.render(mb)
+        out_om = O.render_mmsk(sd, mb, O.OracleCfg(perturb=0.), return_debug=True)
+    mkeys = ('rgb_map', 'acc_map', 'depth_map')
+    report('tpose_renderer_mmsk.Renderer.render', 'tpose_renderer_mmsk.py:99-166',
+           all(biteq(out_rm[k].numpy(), out_om[k].numpy()) for k in mkeys) and set(out_rm.keys()) == set(mkeys),
+           f'rgb/acc/depth bit-equal; {int(out_om["_debug"]["inside"].sum())} samples survive the culling')
+    np.savez_compressed(os.path.join(GOLDEN, 'render_small_mmsk.npz'), n_views=4, msks=mb['msks'][0].numpy(), Ks=mb['Ks'][0].numpy(),
+                        RT=mb['RT'][0].numpy(), H=int(mb['H']), W=int(mb['W']), inside=out_om['_debug']['inside'].numpy(),
+                        **{k: out_rm[k].numpy() for k in mkeys})
+
     # ---------------- novel-pose field (aninerf_s9p stage 2 shapes) -----------------------------
     sd2 = synthetic.make_state_dict(seed=1, num_train_frame=cfg.num_train_frame, num_eval_frame=8)
     cfg.aninerf_animation = True

@@ -157,3 +157,70 @@ def test_network_forward_api(dev):
     assert out['raw'].shape == ref['raw'].shape
     assert float((out['raw'].cpu() - ref['raw']).abs().max()) <= RGB_TOL
     assert abs(out['pbw'].shape[1] - ref['pbw'].shape[1]) <= 2
+
+
+# ---------------------------------------------------------------------------------------------
+# tpose_renderer_mmsk: multi-view silhouette culling ahead of the network
+# ---------------------------------------------------------------------------------------------
+def _mmsk_renderer(dev, sd, **over):
+    from animatable_nerf_b200 import config
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer_mmsk import Renderer
+    cfg = config.make_cfg(perturb=0., **over)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    return Renderer(net.to(dev), cfg)
+
+
+def _golden_mmsk_batch():
+    g, batch, sd = golden_small_case()
+    gm = load_golden('render_small_mmsk.npz')
+    mb = dict(batch)
+    mb['msks'] = torch.from_numpy(gm['msks'])[None]
+    mb['Ks'] = torch.from_numpy(gm['Ks'])[None]
+    mb['RT'] = torch.from_numpy(gm['RT'])[None]
+    mb['H'], mb['W'] = torch.tensor([int(gm['H'])]), torch.tensor([int(gm['W'])])
+    return gm, mb, sd
+
+
+def test_inside_all_views_bit_exact(dev):
+    """prepare_inside_pts through aninerf_inside_all_views vs the REFERENCE's mask (golden) and the oracle
+    on a larger random cloud (incl. points behind cameras / far outside the images)."""
+    gm, mb, sd = _golden_mmsk_batch()
+    r = _mmsk_renderer(dev, sd)
+    pts, _ = O.sample_points(mb['ray_o'], mb['ray_d'], mb['near'], mb['far'], 64)
+    got = r.prepare_inside_pts(pts.to(dev), to_device(mb, dev))
+    assert got.shape == (1, pts.shape[1] * 64)
+    assert np.array_equal(got.cpu().numpy().reshape(-1), gm['inside'])
+    g = torch.Generator().manual_seed(7)
+    cloud = (torch.rand(1, 400000, 1, 3, generator=g) - 0.5) * 8.0
+    ref = O.inside_all_views(cloud.view(1, -1, 3), mb)
+    got = r.prepare_inside_pts(cloud.to(dev), to_device(mb, dev))
+    assert torch.equal(got.cpu(), ref)
+    assert 0 < int(ref.sum()) < ref.numel()
+
+
+def test_mmsk_render_matches_reference_golden(dev):
+    gm, mb, sd = _golden_mmsk_batch()
+    r = _mmsk_renderer(dev, sd)
+    out = r.render(to_device(mb, dev))
+    assert set(out) == {'rgb_map', 'acc_map', 'depth_map'}          # tpose_renderer_mmsk.py:135-139
+    assert all(not v.is_cuda for v in out.values())
+    _check_maps(out, gm)
+    # culled + masked active set is bit-exact: compare the zero pattern of raw with the oracle's
+    dev_out = r.render_device(to_device(mb, dev))
+    ref = O.render_mmsk(sd, mb, O.OracleCfg(perturb=0.), return_debug=True)
+    assert int(dev_out['n_active'].item()) == int(ref['_debug']['chunk_active'].sum())
+
+
+def test_mmsk_chunk_without_survivors_evaluates_nothing(dev):
+    """All-zero silhouettes: no sample reaches the network (no argmin forcing either), maps are the empty render."""
+    gm, mb, sd = _golden_mmsk_batch()
+    mb = dict(mb)
+    mb['msks'] = torch.zeros_like(mb['msks'])
+    r = _mmsk_renderer(dev, sd)
+    dev_out = r.render_device(to_device(mb, dev))
+    assert int(dev_out['n_active'].item()) == 0
+    assert float(dev_out['acc_map'].abs().max()) == 0.0 and float(dev_out['rgb_map'].abs().max()) == 0.0
+    ref = O.render_mmsk(sd, mb, O.OracleCfg(perturb=0.))
+    _check_maps({k: dev_out[k][None] for k in ('rgb_map', 'acc_map', 'depth_map')}, ref)
