@@ -22,6 +22,7 @@
 // Precision modes: NPASS=1 single bf16 product; NPASS=3 "bf16x3": x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // with fp32 accumulation (fp32-equivalent; the blend-weight field needs it for the 1e-5 gate).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -98,7 +99,8 @@ struct MlpArgs {
   const int32_t *index;
   float *raw_out;
   float *sigma_masked_out;
-  unsigned long long *trace;   // bring-up: clock64 timeline of block 0's first unit tile (null = off)
+  unsigned long long *trace;   // bring-up: clock64 timeline of one unit tile of block 0 (null = off)
+  int32_t trace_iter;          // which of block 0's tiles is traced (0 = first); slots 160+i: start of its i-th tile
 };
 
 // trace slots: 0 tile start, 1 PE done; per (layer l, slot t) base 8 + 16*l + 8*t: +0 rows wait begin,
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       const int t = my_slot;
       const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI + t * A_BYTES), a_lo = smem_u32(smem + C::OFF_A_LO + t * A_BYTES);
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-        const bool tracing = args.trace && blockIdx.x == 0 && ut == 0 && lane == 0;
+        const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && lane == 0;
         for (int l = 0; l < F.n_layers; ++l) {
           const int n_pad = F.layers[l].n_pad;
           const int s0 = F.layers[l].step0, n_layer_steps = F.layers[l].n_steps;
@@ -592,10 +594,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     const int row = (warp & 3) * 32 + lane;            // == TMEM lane; warps w and w+4 share a row
     const int half = warp >> 2;                        // which half of the columns this thread owns
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t a_arrive = leader ? bar_a_ready : bar_a_local;   // rows always arrive CTA-locally
+    // rows always arrive CTA-locally (per-warp aggregated arrives were measured slower: the __syncwarp lengthens every
+    // quarter of the epilogue by more than the serialised arrives cost)
+    const uint32_t a_arrive = leader ? bar_a_ready : bar_a_local;
     uint32_t acc_phase = 0;
     for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-      const bool tracing = args.trace && blockIdx.x == 0 && ut == 0 && threadIdx.x == 0;
+      const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
+      if (args.trace && blockIdx.x == 0 && threadIdx.x == 0 && ut / n_units < 90) args.trace[160 + ut / n_units] = (unsigned long long)clock64();
       int64_t gi[NT];
       bool valid[NT];
       float px[NT], py[NT], pz[NT], sigma[NT];
@@ -633,6 +638,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           float *xchg = s_xchg + t * (TILE_M * 4);           // this slot's exchange between the row's two threads
           const uint32_t t_acc = t_lane + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
           float smpl[ANINERF_N_BONES];
+          if (!NERF && last) ANI_TRACE(4);
           if (!NERF && last && half == 0) {
             // initial SMPL weights of this row, fetched while the last layer's MMAs run
 #pragma unroll
@@ -676,6 +682,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               }
             }
           }
+          if (!NERF && last) ANI_TRACE(5);
           ANI_TRACE(8 + 16 * l + 8 * t);
           mbar_wait(bar_acc + 8 * t, acc_phase, 5 + 10 * t + 100 * l);
           tc_fence_after();
@@ -858,6 +865,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         }
         acc_phase ^= 1;
       }
+      ANI_TRACE(3);
     }
   }
 
@@ -1052,6 +1060,8 @@ static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
 }
 
 static unsigned long long *g_trace = nullptr;
+static int g_trace_iter = 0;
+static int g_trace_field = -1;   // -1: every field's kernel writes the trace; else only this field
 
 static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs &a) {
   if (!net) return fail(ANINERF_EINVAL, "%s: null net%s", __func__);
@@ -1071,7 +1081,8 @@ static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs 
   }
   a.f.bias = f.bias;
   a.f.head = f.head;
-  a.trace = g_trace;
+  a.trace = (g_trace_field < 0 || g_trace_field == field) ? g_trace : nullptr;
+  a.trace_iter = g_trace_iter;
   return ANINERF_OK;
 }
 
@@ -1131,6 +1142,10 @@ extern "C" {
 
 int aninerf_debug_set_trace(unsigned long long *device_buf) {
   g_trace = device_buf;
+  const char *e = getenv("ANINERF_TRACE_ITER");   // which of block 0's tiles to trace (default: the first)
+  g_trace_iter = e ? atoi(e) : 0;
+  e = getenv("ANINERF_TRACE_FIELD");
+  g_trace_field = e ? atoi(e) : -1;
   return ANINERF_OK;
 }
 

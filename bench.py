@@ -35,6 +35,23 @@ WORKLOAD = 'aninerf_313 full 1024x1024 frame render (inverse LBS + canonical NeR
 CPU_SAMPLE_RAYS = 1024      # BASELINE config 1: 1024 rays x 64 samples on the CPU
 
 
+def ncu_traffic(kernel_prefix):
+    """DRAM read+write bytes per launch of a kernel from the newest committed ncu --set full summary (profiles/rNN_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            t = json.load(f)['dram_read_plus_write']
+        for k, v in t.items():
+            if k.startswith(kernel_prefix):
+                return v
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
     try:
@@ -324,7 +341,8 @@ def run_b200(args):
     roofline = {
         'bound': 'tensor', 'kernel': 'mlp_kernel<3,false> (blend-weight field, bf16x3)' if dom == 'bw_field_posed' else 'mlp_kernel<1,true> (NeRF field, bf16)',
         'achieved': dom_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': dom_tflops / pk['bf16_tflops_sustained'],
-        'traffic': None, 'peak_source': pk['source'] + ' (sustained bf16: kernel timed inside the step)',
+        'traffic': ncu_traffic('mlp_kernel<3, 0' if dom == 'bw_field_posed' else 'mlp_kernel<1, 1'), 'traffic_unit': 'DRAM bytes per launch (ncu --set full, profiles/)',
+        'peak_source': pk['source'] + ' (sustained bf16: kernel timed inside the step)',
         'algorithmic_flop_per_active_sample': cand[dom], 'active_samples_per_launch': n_active, 'launch_ms': stage_ms[dom],
         'both_mlps': {'tflops': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 if mlp_ms else None,
                       'frac': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'] if mlp_ms else None},

@@ -129,7 +129,7 @@ def trace():
     """clock64 timeline of one tile of each MLP kernel (block 0, first tile)."""
     _, _, batch, _ = small_frame_case(voxel=0.05, H=128, W=128, focal=130.0)
     sd = synthetic.make_state_dict(seed=0)
-    n = 148 * 128 * 4
+    n = int(os.environ.get('ANINERF_TRACE_N', 148 * 128 * 4))
     g = torch.Generator().manual_seed(11)
     lo, hi = batch['tbounds'][0, 0], batch['tbounds'][0, 1]
     pts = (torch.rand(1, n, 3, generator=g) * (hi - lo) + lo).to(dev)
@@ -149,6 +149,8 @@ def trace():
         torch.cuda.synchronize()
         _lib.lib().aninerf_debug_set_trace(None)
         t = buf.cpu().numpy()
+        starts = [int(x) for x in t[160:250] if x]
+        say(f'{name}: tile periods of block 0 (cycles):', [b - a for a, b in zip(starts[:-1], starts[1:])])
         t0 = t[0]
         say(f'{name}: tile start 0, PE done {t[1] - t0}')
         for l in range(9):
@@ -159,14 +161,51 @@ def trace():
                 say(f'  L{l} slot{ts}: mma wait_a {t[b + 4] - t0} woke {t[b + 5] - t0} issued {t[b + 6] - t0} | rows wait {t[b] - t0} '
                     f'woke {t[b + 1] - t0} done {t[b + 2] - t0 if t[b + 2] else 0}  || issue {t[b + 6] - t[b + 5]} '
                     f'epilogue {t[b + 2] - t[b + 1] if t[b + 2] else 0}')
+
+
+def print_trace(name, t):
+    starts = [int(x) for x in t[160:250] if x]
+    per = [b - a for a, b in zip(starts[:-1], starts[1:])]
+    say(f'{name}: {len(starts)} tiles on block 0, mean period {np.mean(per) if per else 0:.0f} cycles; periods {per[:12]} ...')
+    t0 = t[0]
+    say(f'{name}: tile start 0, PE done {t[1] - t0}, smpl gather {t[4] - t0}..{t[5] - t0}, tile done {t[3] - t0}')
+    for l in range(9):
         for ts in range(2):
-            for i in range(12):
-                b = 160 + 48 * ts + 4 * i
-                if t[b] == 0:
-                    continue
-                say(f'    L2 slot{ts} step{i}: wait {t[b + 1] - t[b]} issue {t[b + 2] - t[b + 1]} commit {t[b + 3] - t[b + 2]} '
-                    f'(t={t[b] - t0}..{t[b + 3] - t0})')
+            b = 8 + 16 * l + 8 * ts
+            if t[b + 5] == 0:
+                continue
+            say(f'  L{l} slot{ts}: mma wait_a {t[b + 4] - t0} woke {t[b + 5] - t0} issued {t[b + 6] - t0} | rows wait {t[b] - t0} '
+                f'woke {t[b + 1] - t0} done {t[b + 2] - t0 if t[b + 2] else 0}  || issue {t[b + 6] - t[b + 5]} '
+                f'epilogue {t[b + 2] - t[b + 1] if t[b + 2] else 0}')
+
+
+def trace_frame():
+    """clock64 timeline of a steady-state tile of each MLP kernel inside the bench frame (volume gather + LBS head)."""
+    import bench
+    from animatable_nerf_b200 import frontend
+    frame, cam, sd = bench.build_workload(1024)
+    K, R, T = cam
+    ray_o, ray_d, near, far, mask = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    cfg = config.make_cfg(perturb=0., b200_render_only=True)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    r = Renderer(net, cfg)
+    batch = synthetic.make_render_batch(frame, ray_o, ray_d, near, far, device=dev)
+    r.render_device(batch, want_bw=False)
+    torch.cuda.synchronize()
+    buf = torch.zeros(256, dtype=torch.int64, device=dev)
+    for name, field in (('BW x3 (frame)', 0), ('NERF x1 (frame)', 2)):
+        os.environ['ANINERF_TRACE_FIELD'] = str(field)
+        buf.zero_()
+        _lib.lib().aninerf_debug_set_trace(buf.data_ptr())
+        r.render_device(batch, want_bw=False)
+        torch.cuda.synchronize()
+        _lib.lib().aninerf_debug_set_trace(None)
+        print_trace(name, buf.cpu().numpy())
 
 
 if 'trace' in sys.argv[1:]:
     section('trace', trace)
+if 'trace_frame' in sys.argv[1:]:
+    section('trace_frame', trace_frame)
