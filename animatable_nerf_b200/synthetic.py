@@ -184,6 +184,25 @@ def make_rays(frame: dict, H: int = 1024, W: int = 1024, focal: float = 1070.0, 
     return make_camera(frame, H, W, focal, distance, azimuth)
 
 
+def make_train_batch(frame: dict, ray_o, ray_d, near, far, n_rays: int = 1024, ray_seed: int = 3, rgb_seed: int = 4,
+                     jitter_seed: int = 5, device='cpu'):
+    """A training batch as lib/datasets/tpose_dataset.py:236-277 collates it: `n_rays` seeded
+    rays of the box-hitting set, target colours U(0,1), `mask_at_box`, and the stratified jitter `t_rand` drawn on the
+    CPU generator as tpose_renderer.py:35 does.  Returns (batch, t_rand (1, n_rays, 64))."""
+    rs = np.random.RandomState(ray_seed)
+    total = np.asarray(near).shape[0]
+    sel = np.sort(rs.choice(total, size=min(n_rays, total), replace=False))
+    b = make_render_batch(frame, np.asarray(ray_o)[sel], np.asarray(ray_d)[sel], np.asarray(near)[sel], np.asarray(far)[sel], device=device)
+    n = sel.shape[0]
+    b['rgb'] = torch.from_numpy(np.random.RandomState(rgb_seed).uniform(0, 1, (1, n, 3)).astype(np.float32)).to(device)
+    m = np.ones((1, n), dtype=bool)
+    m[0, ::17] = False                       # a few sampled pixels outside the box mask (if_nerf_data_utils.py:283-292)
+    b['mask_at_box'] = torch.from_numpy(m).to(device)
+    g = torch.Generator().manual_seed(jitter_seed)
+    t_rand = torch.rand(1, n, 64, generator=g)
+    return b, t_rand
+
+
 # ---------------------------------------------------------------------------------------------
 # training-view silhouettes for the novel-view renderer (tpose_renderer_mmsk)
 # ---------------------------------------------------------------------------------------------

@@ -349,14 +349,15 @@ def raw2outputs(raw, z_vals, white_bkgd=False):
 # ----------------------------------------------------------------------------
 # the renderer  -- tpose_renderer.py:71-186
 # ----------------------------------------------------------------------------
-def render(sd, batch, cfg=None, t_rand=None, return_debug=False):
-    """Renderer.render: 2048-ray chunks -> sample -> Network.forward -> raw2outputs; concat on dim 1."""
+def render(sd, batch, cfg=None, t_rand=None, return_debug=False, grad=False):
+    """Renderer.render: 2048-ray chunks -> sample -> Network.forward -> raw2outputs; concat on dim 1.
+    grad=True keeps the autograd graph (training, tpose_renderer.py:154 keeps device tensors with grad)."""
     cfg = cfg or OracleCfg()
     ray_o, ray_d, near, far = batch['ray_o'], batch['ray_d'], batch['near'], batch['far']
     R = ray_o.shape[1]
     S = cfg.N_samples
     outs = []
-    with torch.no_grad():
+    with torch.set_grad_enabled(bool(grad)):
         for i in range(0, R, cfg.chunk):
             o, d = ray_o[:, i:i + cfg.chunk], ray_d[:, i:i + cfg.chunk]
             tr = None if t_rand is None else t_rand[:, i:i + cfg.chunk]
@@ -383,6 +384,31 @@ def render(sd, batch, cfg=None, t_rand=None, return_debug=False):
         dbg['chunk_active'] = torch.tensor([int(r['_debug']['pind'].sum()) for r in outs])
         out['_debug'] = dbg
     return out
+
+
+# ----------------------------------------------------------------------------
+# the training step  -- lib/train/trainers/tpose_trainer.py:21-73, trainer.py:54-68
+# ----------------------------------------------------------------------------
+def train_loss(sd, batch, cfg=None, t_rand=None):
+    """NetworkWrapper.forward: loss = smooth_l1(pbw, tbw) + mse(rgb_map[mask], rgb[mask]).  `sd` holds the
+    parameters (requires_grad leaves for gradients).  Returns (ret, loss, scalar_stats)."""
+    cfg = cfg or OracleCfg()
+    ret = render(sd, batch, cfg, t_rand=t_rand, grad=True)
+    bw_loss = F.smooth_l1_loss(ret['pbw'], ret['tbw'])
+    mask = batch['mask_at_box']
+    img_loss = torch.mean((ret['rgb_map'][mask] - batch['rgb'][mask]) ** 2)
+    loss = bw_loss + img_loss
+    return ret, loss, {'bw_loss': bw_loss, 'img_loss': img_loss, 'loss': loss}
+
+
+def train_step_grads(sd, batch, cfg=None, t_rand=None, clip=40.0):
+    """One Trainer.train iteration up to the optimizer (trainer.py:62-66): zero_grad, backward,
+    clip_grad_value_(40).  Returns (loss stats as floats, {name: grad})."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    _, loss, stats = train_loss(params, batch, cfg, t_rand)
+    loss.backward()
+    grads = {k: (v.grad.clamp(-clip, clip) if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
+    return {k: float(v) for k, v in stats.items()}, grads
 
 
 # ----------------------------------------------------------------------------

@@ -75,6 +75,11 @@ def load(cfg_file='configs/aninerf_313.yaml', overrides=()):
         from lib.utils import blend_utils
         from lib.networks import embedder
         from lib.networks.renderer import tpose_renderer_mmsk as mmsk_mod
+        trainer_mod = None
+        try:
+            from lib.train.trainers import tpose_trainer as trainer_mod
+        except Exception as e:  # noqa: BLE001  (optional: needs the tensorboardX / trimesh stubs)
+            print('reference_import: tpose_trainer not importable:', e)
     finally:
         sys.argv = saved_argv
         os.chdir(saved_cwd)
@@ -84,5 +89,5 @@ def load(cfg_file='configs/aninerf_313.yaml', overrides=()):
             os.environ['CUDA_VISIBLE_DEVICES'] = saved_cvd
     _loaded = types.SimpleNamespace(cfg=cfg, Network=net_mod.Network, Renderer=ren_mod.Renderer,
                                     net_mod=net_mod, dutils=dutils, nerf_net_utils=nerf_net_utils,
-                                    blend_utils=blend_utils, embedder=embedder, MmskRenderer=mmsk_mod.Renderer)
+                                    blend_utils=blend_utils, embedder=embedder, MmskRenderer=mmsk_mod.Renderer, trainer_mod=trainer_mod)
     return _loaded

@@ -186,6 +186,44 @@ def main():
                         RT=mb['RT'][0].numpy(), H=int(mb['H']), W=int(mb['W']), inside=out_om['_debug']['inside'].numpy(),
                         **{k: out_rm[k].numpy() for k in mkeys})
 
+    # ---------------- training step (tpose_trainer.NetworkWrapper + Trainer.train up to the optimizer) ---------
+    if ref.trainer_mod is not None:
+        tb, t_rand = synthetic.make_train_batch(small, ray_o, ray_d, near, far, n_rays=512)
+        cfg.perturb = 1.
+        net.train()
+        net.zero_grad()
+        cwd = os.getcwd()
+        os.chdir(reference_import.REF)          # make_renderer loads cfg.renderer_path relative to the reference root
+        try:
+            wrapper = ref.trainer_mod.NetworkWrapper(net)
+        finally:
+            os.chdir(cwd)
+        torch.manual_seed(5)
+        # the reference draws the jitter with torch.rand on the global CPU generator (tpose_renderer.py:35)
+        t_rand = torch.rand(1, tb['ray_o'].shape[1], 64)
+        torch.manual_seed(5)
+        _, loss_r, stats_r, _ = wrapper(tb)
+        loss_r.mean().backward()
+        torch.nn.utils.clip_grad_value_(net.parameters(), 40)
+        grads_r = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in net.named_parameters()}
+        stats_o, grads_o = O.train_step_grads(sd, tb, O.OracleCfg(perturb=1.), t_rand=t_rand)
+        ok = all(biteq(grads_r[k].numpy(), grads_o[k].numpy()) for k in grads_r) and \
+            all(float(stats_r[k]) == stats_o[k] for k in ('bw_loss', 'img_loss', 'loss'))
+        worst = max(maxdiff(grads_r[k], grads_o[k]) for k in grads_r)
+        report('tpose_trainer step: loss + 46 parameter gradients', 'tpose_trainer.py:21-73, trainer.py:62-66', ok,
+               f'bit-equal (loss {stats_o["loss"]:.6f} = bw {stats_o["bw_loss"]:.3e} + img {stats_o["img_loss"]:.6f}); max grad diff {worst:.1e}')
+        np.savez_compressed(os.path.join(GOLDEN, 'train_step_small.npz'), n_rays=512, t_rand=t_rand.numpy(),
+                            ray_o=tb['ray_o'][0].numpy(), ray_d=tb['ray_d'][0].numpy(), near=tb['near'][0].numpy(), far=tb['far'][0].numpy(),
+                            rgb=tb['rgb'][0].numpy(), mask_at_box=tb['mask_at_box'][0].numpy(),
+                            **{'stat_' + k: np.float32(float(stats_r[k])) for k in ('bw_loss', 'img_loss', 'loss')},
+                            **{'grad_' + k: grads_r[k].numpy() for k in ('bw_fc.weight', 'bw_fc.bias', 'bw_linears.0.bias', 'bw_latent.weight',
+                                                                         'tpose_human.alpha_fc.weight', 'tpose_human.rgb_fc.weight',
+                                                                         'tpose_human.pts_linears.0.bias', 'tpose_human.pts_linears.7.bias',
+                                                                         'tpose_human.nf_latent.weight', 'tpose_human.view_fc.bias')},
+                            **{'gradnorm_' + k: np.float32(float(grads_r[k].norm())) for k in grads_r})
+        cfg.perturb = 0.
+        net.zero_grad()
+
     # ---------------- novel-pose field (aninerf_s9p stage 2 shapes) -----------------------------
     sd2 = synthetic.make_state_dict(seed=1, num_train_frame=cfg.num_train_frame, num_eval_frame=8)
     cfg.aninerf_animation = True
