@@ -55,6 +55,17 @@ class Silhouettes(C.Structure):
     _fields_ = [('msks', C.c_void_p), ('Ks', C.c_void_p), ('RT', C.c_void_p), ('n_views', C.c_int32), ('H', C.c_int32), ('W', C.c_int32)]
 
 
+class GemmSeg(C.Structure):
+    _fields_ = [('A', C.c_void_p), ('a_row_stride', C.c_int64), ('a_k_stride', C.c_int64), ('B', C.c_void_p), ('b_row_stride', C.c_int64),
+                ('b_k_stride', C.c_int64), ('K', C.c_int32)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [('seg', GemmSeg * 2), ('n_seg', C.c_int32), ('M', C.c_int32), ('N', C.c_int32), ('C', C.c_void_p), ('ldc', C.c_int64),
+                ('bias', C.c_void_p), ('relu_mask', C.c_void_p), ('ld_mask', C.c_int64), ('relu', C.c_int32), ('accumulate', C.c_int32),
+                ('split_k', C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/aninerf_b200.h declares
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 PROTOTYPES = {
@@ -85,6 +96,24 @@ PROTOTYPES = {
     'aninerf_render_rays_culled': (_I32, [_VP, C.POINTER(Frame), C.POINTER(RenderParams), C.POINTER(Silhouettes), _VP, _VP, _VP, _VP, _VP,
                                           _VP, _I64, C.POINTER(RenderOutputs), _VP, _I64, _VP]),
     'aninerf_inside_all_views': (_I32, [_VP, _I64, C.POINTER(Silhouettes), _VP, _VP]),
+    'aninerf_front_end_workspace_bytes': (_I64, [_I64, _I32, _I64]),
+    'aninerf_front_end': (_I32, [C.POINTER(Frame), C.POINTER(RenderParams), _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
+                                 _VP, _I64, _VP]),
+    'aninerf_gemm_workspace_bytes': (_I64, [C.POINTER(Gemm)]),
+    'aninerf_gemm_x3': (_I32, [C.POINTER(Gemm), _VP, _I64, _VP]),
+    'aninerf_colsum': (_I32, [_VP, _I64, _I64, _I32, _VP, _I32, _VP, _I64, _VP]),
+    'aninerf_pe_forward': (_I32, [_VP, _I64, _I32, _VP, _I64, _VP]),
+    'aninerf_pe_backward': (_I32, [_VP, _VP, _I64, _I64, _I32, _VP, _I32, _VP]),
+    'aninerf_bw_softmax_forward': (_I32, [_VP, _I64, _VP, _I64, _VP, _VP]),
+    'aninerf_bw_softmax_backward': (_I32, [_VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_inverse_lbs_backward': (_I32, [_VP, _VP, _VP, _VP, _I64, _VP, _I32, _VP]),
+    'aninerf_sample_blend_weights_backward': (_I32, [_VP, _I64, _VP, C.POINTER(_I32), _VP, _VP, _VP, _I32, _VP]),
+    'aninerf_nerf_tail_forward': (_I32, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_nerf_tail_backward': (_I32, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_composite_backward': (_I32, [_VP, _VP, _I64, _I32, _I32, _VP, _VP]),
+    'aninerf_img_loss': (_I32, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_select_rows': (_I32, [_VP, _VP, _I32, _F, _VP, _VP, _VP]),
+    'aninerf_bw_loss': (_I32, [_VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     'aninerf_query_workspace_bytes': (_I64, [_I64, _I64]),
     'aninerf_query_alpha': (_I32, [_VP, C.POINTER(Frame), _VP, _I64, _I64, _F, _I32, _I32, _VP, _VP, _VP, _I64, _VP]),
 }

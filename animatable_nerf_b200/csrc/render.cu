@@ -229,6 +229,37 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
 
 extern "C" {
 
+int64_t aninerf_front_end_workspace_bytes(int64_t n_rays, int32_t n_samples, int64_t pbw_voxels) {
+  Carver c(nullptr, 0);
+  RenderScratch s;
+  return carve_render(c, n_rays, n_samples, 0, pbw_voxels, 0, s);
+}
+
+// The front end of the fused path on its own (training step): sample -> pose -> pnorm mask -> per-chunk argmin forcing ->
+// stable compaction.  Outputs have room for n_rays*S rows; *n_active / chunk_offsets stay on the device.
+int aninerf_front_end(const aninerf_frame *fr, const aninerf_render_params *pr, const float *ray_o, const float *ray_d, const float *near,
+                      const float *far, const float *t_vals, const float *t_rand, int64_t n_rays, int32_t *index, float *ppts, float *viewdir,
+                      float *dists, float *z_vals, int32_t *n_active, int32_t *chunk_offsets, void *workspace, int64_t workspace_bytes,
+                      void *stream) {
+  ANI_CHECK_ARG(fr && pr && ray_o && ray_d && near && far && t_vals && index && ppts && viewdir && dists && n_active && workspace && n_rays > 0);
+  ANI_CHECK_ARG(fr->R && fr->Th && fr->pbw && fr->pbounds);
+  const int S = pr->n_samples;
+  ANI_CHECK_ARG(S == 32 || S == 64);
+  ANI_CHECK_ARG(pr->chunk_rays > 0 && ((int64_t)pr->chunk_rays * S) % 2048 == 0 && n_rays * S < (int64_t)2147483647);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t pv = (int64_t)fr->pbw_dims[0] * fr->pbw_dims[1] * fr->pbw_dims[2];
+  Carver c(workspace, workspace_bytes);
+  RenderScratch s;
+  if (carve_render(c, n_rays, S, 0, pv, 0, s) > workspace_bytes) return fail(ANINERF_ENOMEM, "%s: workspace too small%s", __func__);
+  int rc;
+  if ((rc = launch_split_volume(fr->pbw, fr->pbw_dims, s.w24_p, s.dist_p, st))) return rc;
+  if ((rc = launch_front_end(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, pr->chunk_rays, fr->R, fr->Th, fr->pbounds, fr->pbw_dims, s.dist_p,
+                             pr->norm_th, s.fb, index, ppts, viewdir, dists, n_active, chunk_offsets, nullptr, st)))
+    return rc;
+  if (z_vals) return aninerf_sample_points(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, nullptr, z_vals, nullptr, stream);
+  return ANINERF_OK;
+}
+
 int aninerf_profile_enable(int32_t on) {
   g_profile = on != 0;
   return ANINERF_OK;

@@ -1,0 +1,363 @@
+"""Drop-in for `lib/train/trainers/tpose_trainer.py`: `NetworkWrapper(net).forward(batch)` returns
+`(ret, loss, scalar_stats, image_stats)` with `loss = smooth_l1(pbw, tbw) + mse(rgb_map[mask], rgb[mask])`
+(tpose_trainer.py:21-73), and `loss.backward()` fills the `.grad` of every `Network` parameter exactly as
+`Trainer.train` expects (lib/train/trainers/trainer.py:62-66) -- but forward AND backward run on this library's
+kernels: the front end of the fused render path, then layer-by-layer split-precision tcgen05 GEMMs
+(csrc/gemm_x3.cu: forward, data gradient and weight gradient of every 1x1 Conv1d, fp32-equivalent) and the
+per-point forward/backward kernels of csrc/train_ops.cu.  Activations are kept in fp32, so losses and gradients
+match the fp32 reference to ~1e-5 relative.  PyTorch only owns the memory, the parameter / optimizer objects
+(torch.optim.Adam as in lib/train/optimizer.py:12-27) and NCCL (`allreduce_gradients`).
+
+Gradient flow (what torch.autograd derives for tpose_nerf_network.py:139-215):
+  img loss -> raw2outputs -> tail -> NeRF heads/trunk -> PE(tpose) -----------.
+  bw loss  -> tbw -> softmax -> canonical blend-weight trunk -> PE(tpose) ----+--> d tpose -> inverse LBS -> d pbw
+           -> tbw -> log(init_tbw) -> trilinear sampling at tpose ------------'                               |
+  bw loss  -> pbw ---------------------------------------------------------------------------------------------+--> softmax -> posed trunk
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, config
+from . import train_ops as T
+from .train_ops import Op
+from .tpose_nerf_network import _frame_struct
+from .tpose_renderer import Renderer
+
+
+def _w2(p):
+    """Conv1d weight (out, in, 1) -> (out, in) view"""
+    return p.detach().view(p.shape[0], p.shape[1])
+
+
+class _Grads:
+    """One flat fp32 gradient buffer with a view per parameter (the allreduce payload)."""
+
+    def __init__(self, net):
+        params = list(net.named_parameters())
+        dev = params[0][1].device
+        self.flat = torch.zeros(sum(p.numel() for _, p in params), device=dev)
+        self.views, off = {}, 0
+        for name, p in params:
+            self.views[name] = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+
+    def w(self, name):
+        v = self.views[name]
+        return v.view(v.shape[0], v.shape[1]) if v.dim() == 3 else v
+
+
+class _Trunk:
+    """8 x (1x1 conv + ReLU) with the skip concat after layer 4 (tpose_nerf_network.py:68-72, 256-260): forward keeping every
+    activation, backward producing weight / bias / latent gradients and (optionally) the gradient of the PE input."""
+
+    def __init__(self, sd, prefix, lat_cols, grads: _Grads):
+        self.W = [_w2(sd[f'{prefix}.{i}.weight']) for i in range(8)]
+        self.b = [sd[f'{prefix}.{i}.bias'].detach() for i in range(8)]
+        self.gW = [grads.w(f'{prefix}.{i}.weight') for i in range(8)]
+        self.gb = [grads.views[f'{prefix}.{i}.bias'] for i in range(8)]
+        self.lat = lat_cols          # number of latent input channels after the 63 PE channels (128 or 0)
+        self.hid0 = 63 + lat_cols    # first hidden column of the skip layer's weight
+
+    def forward(self, pe, lat):
+        """pe (n,>=63) fp32 [PE in the first 63 columns]; lat (1,128) or None -> list H, H[l] = input of layer l, H[8] = output"""
+        n, dev = pe.shape[0], pe.device
+        H = [None] * 9
+        self.beff = [None] * 8
+        for l in range(8):
+            bias = self.b[l]
+            if self.lat and l in (0, 5):
+                bias = torch.empty(1, 256, device=dev)          # latent code folded into the bias: b + W[:, 63:191] @ latent
+                T.gemm([(Op(lat), Op(self.W[l][:, 63:63 + self.lat]))], bias, bias=self.b[l])
+                self.beff[l] = bias
+            if l == 0:
+                segs = [(Op(pe[:, :63]), Op(self.W[0][:, :63]))]
+            elif l == 5:
+                segs = [(Op(pe[:, :63]), Op(self.W[5][:, :63])), (Op(H[5]), Op(self.W[5][:, self.hid0:]))]
+            else:
+                segs = [(Op(H[l]), Op(self.W[l]))]
+            H[l + 1] = T.gemm(segs, torch.empty(n, 256, device=dev), bias=bias, relu=True)
+        self.pe, self.H, self.latv = pe, H, lat
+        return H[8]
+
+    def backward(self, dZ, g_lat, d_pe):
+        """dZ (n,256): gradient of layer 7's pre-activation.  g_lat (1,128) gradient row of the latent code (accumulated) or None.
+        d_pe (n,>=63) or None: receives the gradient of the PE input (written, not accumulated)."""
+        n, dev = dZ.shape[0], dZ.device
+        H, pe = self.H, self.pe
+        sk = T.split_for(n)
+        for l in range(7, -1, -1):
+            W, gW = self.W[l], self.gW[l]
+            # weight gradients  dW[seg] += dZ^T @ X_seg
+            if l == 0:
+                T.gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, split_k=sk)
+            elif l == 5:
+                T.gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, split_k=sk)
+                T.gemm([(Op(dZ).T, Op(H[5]).T)], gW[:, self.hid0:], accumulate=True, split_k=sk)
+            else:
+                T.gemm([(Op(dZ).T, Op(H[l]).T)], gW, accumulate=True, split_k=sk)
+            # bias (and folded latent) gradients
+            if self.lat and l in (0, 5):
+                db = T.colsum(dZ, torch.empty(1, 256, device=dev))
+                self.gb[l].add_(db.view(-1))
+                Wl = W[:, 63:63 + self.lat]
+                T.gemm([(Op(db).T, Op(self.latv).T)], gW[:, 63:63 + self.lat], accumulate=True)        # d W_lat += db (x) latent
+                T.gemm([(Op(db), Op(Wl).T)], g_lat, accumulate=True)                                  # d latent += db @ W_lat
+            else:
+                T.colsum(dZ, self.gb[l], accumulate=True)
+            # data gradients
+            if d_pe is not None and l in (0, 5):
+                T.gemm([(Op(dZ), Op(W[:, :63]).T)], d_pe[:, :63], accumulate=(l == 0))
+            if l > 0:
+                Wh = W[:, self.hid0:] if l == 5 else W
+                dZ = T.gemm([(Op(dZ), Op(Wh).T)], torch.empty(n, 256, device=dev), relu_mask=H[l])
+        return d_pe
+
+
+class TrainStep:
+    """Forward + backward of one training batch on the library's kernels; holds no state between calls except scratch."""
+
+    def __init__(self, net, cfg=None):
+        self.net = net
+        self.cfg = cfg if cfg is not None else getattr(net, 'cfg', None) or config.global_cfg()
+        self._renderer = Renderer(net, self.cfg)
+        self._ws = None
+
+    def _workspace(self, nbytes, dev):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    @torch.no_grad()
+    def run(self, batch, t_rand=None):
+        """Returns (ret, stats, grads): ret = the Renderer.render training contract (device tensors), stats = device scalars
+        bw_loss / img_loss / loss, grads = _Grads (d loss / d parameter)."""
+        cfg, net, L = self.cfg, self.net, _lib.lib()
+        sd = dict(net.named_parameters())
+        if 'novel_pose_bw.bw_fc.weight' in sd and config.get(cfg, 'test_novel_pose'):
+            raise _lib.AninerfError('tpose_trainer trains the frame-indexed fields; the novel-pose stage is aninerf_animation_trainer')
+        ray_o = batch['ray_o']
+        _lib.require_cuda(ray_o, "batch['ray_o']")
+        dev = ray_o.device
+        st = _lib.stream_ptr(dev)
+        R = ray_o.shape[1]
+        S = int(config.get(cfg, 'N_samples'))
+        n = R * S
+        o, d = _lib.f32c(ray_o.reshape(-1, 3)), _lib.f32c(batch['ray_d'].reshape(-1, 3))
+        near, far = _lib.f32c(batch['near'].reshape(-1)), _lib.f32c(batch['far'].reshape(-1))
+        fr, keep = _frame_struct(batch, need_tbw=True)
+        pr = _lib.RenderParams(n_samples=S, chunk_rays=_lib.CHUNK_RAYS, norm_th=float(config.get(cfg, 'norm_th')),
+                               white_bkgd=int(bool(config.get(cfg, 'white_bkgd'))), novel_pose=0, want_bw=1, bw_precision=3, nerf_precision=3)
+        tv = self._renderer._tv(S, dev)
+        tr = _lib.f32c(t_rand.reshape(R, S).to(dev)) if t_rand is not None else None
+        latent_index = int(torch.as_tensor(batch['latent_index']).reshape(-1)[0])
+
+        # ---- front end: samples -> pose space -> pnorm mask -> per-chunk argmin forcing -> compaction -----------------
+        n_chunks = (R + _lib.CHUNK_RAYS - 1) // _lib.CHUNK_RAYS
+        index = torch.empty(n, dtype=torch.int32, device=dev)
+        ppts_all, vd_all, dists_all = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
+        z_vals = torch.empty(R, S, device=dev)
+        n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+        chunk_offsets = torch.zeros(n_chunks + 1, dtype=torch.int32, device=dev)
+        pv = int(fr.pbw_dims[0]) * fr.pbw_dims[1] * fr.pbw_dims[2]
+        ws_bytes = L.aninerf_front_end_workspace_bytes(R, S, pv)
+        ws = self._workspace(ws_bytes, dev)
+        _lib.check(L.aninerf_front_end(C.byref(fr), C.byref(pr), _lib.ptr(o), _lib.ptr(d), _lib.ptr(near), _lib.ptr(far), _lib.ptr(tv), _lib.ptr(tr),
+                                       R, _lib.ptr(index), _lib.ptr(ppts_all), _lib.ptr(vd_all), _lib.ptr(dists_all), _lib.ptr(z_vals),
+                                       _lib.ptr(n_active), _lib.ptr(chunk_offsets), _lib.ptr(ws), ws_bytes, st))
+        m = int(n_active.item())                      # the reference syncs here too (boolean indexing, tpose_nerf_network.py:155-157)
+        index, ppts, viewdir, dists = index[:m], ppts_all[:m], vd_all[:m], dists_all[:m]
+
+        G = _Grads(net)
+        A = _lib.f32c(batch['A'].reshape(24, 4, 4))
+        pvol, tvol = _lib.f32c(batch['pbw'][0]), _lib.f32c(batch['tbw'][0])
+        pb, tb = _lib.f32c(batch['pbounds'].reshape(2, 3)), _lib.f32c(batch['tbounds'].reshape(2, 3))
+        bw_lat, nf_lat = sd['bw_latent.weight'].detach(), sd['tpose_human.nf_latent.weight'].detach()
+        lat_p, lat_c, lat_n = bw_lat[latent_index + 1:latent_index + 2], bw_lat[0:1], nf_lat[latent_index:latent_index + 1]
+        Wfc, bfc = _w2(sd['bw_fc.weight']), sd['bw_fc.bias'].detach()
+
+        def e(*shape):
+            return torch.empty(*shape, device=dev)
+
+        # ---- blend-weight field at the posed points + inverse LBS (tpose_nerf_network.py:79-100) ------------------------
+        pe_p = T.pe_forward(ppts, 10, e(m, 64))
+        trunk_p = _Trunk(sd, 'bw_linears', 128, G)
+        h8p = trunk_p.forward(pe_p, lat_p)
+        delta_p = T.gemm([(Op(h8p), Op(Wfc))], e(m, 24), bias=bfc)
+        init_p = T.sample_volume(ppts, pvol, pb, e(m, 25))
+        pbw = T.bw_softmax_forward(init_p, delta_p, e(m, 24))
+        tpts = T.inverse_lbs(ppts, pbw, A, e(m, 3))
+        # ---- blend-weight field at the canonical points, latent index 0 (:163-170) --------------------------------------
+        pe_c = T.pe_forward(tpts, 10, e(m, 64))
+        trunk_c = _Trunk(sd, 'bw_linears', 128, G)
+        h8c = trunk_c.forward(pe_c, lat_c)
+        delta_c = T.gemm([(Op(h8c), Op(Wfc))], e(m, 24), bias=bfc)
+        init_t = T.sample_volume(tpts, tvol, tb, e(m, 25))
+        tbw = T.bw_softmax_forward(init_t, delta_c, e(m, 24))
+        # ---- canonical NeRF field (:252-275) ----------------------------------------------------------------------------
+        p = 'tpose_human.'
+        trunk_n = _Trunk(sd, p + 'pts_linears', 0, G)
+        h8n = trunk_n.forward(pe_c, None)
+        Wa, Wf, Wl, Wv, Wr = (_w2(sd[p + k + '.weight']) for k in ('alpha_fc', 'feature_fc', 'latent_fc', 'view_fc', 'rgb_fc'))
+        ba, bf, bl, bv, br = (sd[p + k + '.bias'].detach() for k in ('alpha_fc', 'feature_fc', 'latent_fc', 'view_fc', 'rgb_fc'))
+        sigma = T.gemm([(Op(h8n), Op(Wa))], e(m, 1), bias=ba)
+        feat = T.gemm([(Op(h8n), Op(Wf))], e(m, 256), bias=bf)
+        bl_eff = T.gemm([(Op(lat_n), Op(Wl[:, 256:]))], e(1, 256), bias=bl)
+        f2 = T.gemm([(Op(feat), Op(Wl[:, :256]))], e(m, 256), bias=bl_eff)
+        pe_v = T.pe_forward(viewdir, 4, e(m, 32))
+        hv = T.gemm([(Op(f2), Op(Wv[:, :256])), (Op(pe_v[:, :27]), Op(Wv[:, 256:]))], e(m, 128), bias=bv, relu=True)
+        rgb = T.gemm([(Op(hv), Op(Wr))], e(m, 3), bias=br)
+        # ---- tail, compositing, losses ------------------------------------------------------------------------------------
+        raw = torch.zeros(n, 4, device=dev)
+        sigma_masked = e(m)
+        _lib.check(L.aninerf_nerf_tail_forward(_lib.ptr(sigma), _lib.ptr(rgb), _lib.ptr(tpts), _lib.ptr(tb), _lib.ptr(dists), _lib.ptr(index), m,
+                                               _lib.ptr(raw), _lib.ptr(sigma_masked), st))
+        rgb_map, acc_map, depth_map = e(R, 3), e(R), e(R)
+        _lib.check(L.aninerf_composite(_lib.ptr(raw), _lib.ptr(z_vals), R, S, pr.white_bkgd, _lib.ptr(rgb_map), _lib.ptr(acc_map),
+                                       _lib.ptr(depth_map), None, None, st))
+        sel = torch.empty(m, dtype=torch.uint8, device=dev)
+        n_sel = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(L.aninerf_select_rows(_lib.ptr(sigma_masked), _lib.ptr(chunk_offsets), n_chunks, float(config.get(cfg, 'train_th')),
+                                         _lib.ptr(sel), _lib.ptr(n_sel), st))
+        losses = torch.zeros(2, device=dev)
+        d_pbw, d_tbw = e(m, 24), e(m, 24)
+        _lib.check(L.aninerf_bw_loss(_lib.ptr(pbw), _lib.ptr(tbw), _lib.ptr(sel), _lib.ptr(n_sel), m, _lib.ptr(losses[0:1]), _lib.ptr(d_pbw),
+                                     _lib.ptr(d_tbw), st))
+        rgb_gt = _lib.f32c(batch['rgb'].reshape(R, 3))
+        mask = batch['mask_at_box'].reshape(R).to(torch.uint8).contiguous()
+        d_rgb_map = e(R, 3)
+        _lib.check(L.aninerf_img_loss(_lib.ptr(rgb_map), _lib.ptr(rgb_gt), _lib.ptr(mask), R, _lib.ptr(losses[1:2]), _lib.ptr(d_rgb_map), st))
+
+        # ================================= backward =========================================================================
+        d_raw = e(n, 4)
+        _lib.check(L.aninerf_composite_backward(_lib.ptr(raw), _lib.ptr(d_rgb_map), R, S, pr.white_bkgd, _lib.ptr(d_raw), st))
+        d_sigma, d_rgb = e(m, 1), e(m, 3)
+        _lib.check(L.aninerf_nerf_tail_backward(_lib.ptr(d_raw), _lib.ptr(raw), _lib.ptr(index), _lib.ptr(sigma_masked), _lib.ptr(tpts), _lib.ptr(tb),
+                                                _lib.ptr(dists), m, _lib.ptr(d_sigma), _lib.ptr(d_rgb), st))
+        sk = T.split_for(m)
+        gw, gv = G.w, G.views
+        # NeRF heads
+        T.gemm([(Op(d_rgb).T, Op(hv).T)], gw(p + 'rgb_fc.weight'), accumulate=True, split_k=sk)
+        T.colsum(d_rgb, gv[p + 'rgb_fc.bias'], accumulate=True)
+        dzv = T.gemm([(Op(d_rgb), Op(Wr).T)], e(m, 128), relu_mask=hv)
+        gWv = gw(p + 'view_fc.weight')
+        T.gemm([(Op(dzv).T, Op(f2).T)], gWv[:, :256], accumulate=True, split_k=sk)
+        T.gemm([(Op(dzv).T, Op(pe_v[:, :27]).T)], gWv[:, 256:], accumulate=True, split_k=sk)
+        T.colsum(dzv, gv[p + 'view_fc.bias'], accumulate=True)
+        d_f2 = T.gemm([(Op(dzv), Op(Wv[:, :256]).T)], e(m, 256))
+        gWl = gw(p + 'latent_fc.weight')
+        T.gemm([(Op(d_f2).T, Op(feat).T)], gWl[:, :256], accumulate=True, split_k=sk)
+        dbl = T.colsum(d_f2, e(1, 256))
+        gv[p + 'latent_fc.bias'].add_(dbl.view(-1))
+        T.gemm([(Op(dbl).T, Op(lat_n).T)], gWl[:, 256:], accumulate=True)
+        T.gemm([(Op(dbl), Op(Wl[:, 256:]).T)], gv[p + 'nf_latent.weight'][latent_index:latent_index + 1], accumulate=True)
+        d_feat = T.gemm([(Op(d_f2), Op(Wl[:, :256]).T)], e(m, 256))
+        T.gemm([(Op(d_feat).T, Op(h8n).T)], gw(p + 'feature_fc.weight'), accumulate=True, split_k=sk)
+        T.colsum(d_feat, gv[p + 'feature_fc.bias'], accumulate=True)
+        T.gemm([(Op(d_sigma).T, Op(h8n).T)], gw(p + 'alpha_fc.weight'), accumulate=True, split_k=sk)
+        T.colsum(d_sigma, gv[p + 'alpha_fc.bias'], accumulate=True)
+        dz = T.gemm([(Op(d_feat), Op(Wf).T)], e(m, 256))
+        T.gemm([(Op(d_sigma), Op(Wa).T)], dz, accumulate=True, relu_mask=h8n)
+        d_pe = torch.zeros(m, 64, device=dev)
+        trunk_n.backward(dz, None, d_pe)
+        d_tpts = T.pe_backward(tpts, d_pe, 10, e(m, 3), False)
+        # canonical blend-weight field
+        d_delta, d_init = e(m, 24), e(m, 24)
+        T.bw_softmax_backward(init_t, tbw, d_tbw, d_delta, d_init)
+        gWfc, gbfc = gw('bw_fc.weight'), gv['bw_fc.bias']
+        T.gemm([(Op(d_delta).T, Op(h8c).T)], gWfc, accumulate=True, split_k=sk)
+        T.colsum(d_delta, gbfc, accumulate=True)
+        dz = T.gemm([(Op(d_delta), Op(Wfc).T)], e(m, 256), relu_mask=h8c)
+        g_bw_lat = gv['bw_latent.weight']
+        trunk_c.backward(dz, g_bw_lat[0:1], d_pe)
+        T.pe_backward(tpts, d_pe, 10, d_tpts, True)
+        T.sample_volume_backward(tpts, tvol, tb, d_init, d_tpts, True)
+        # inverse LBS: d tpose -> d pbw (added to the bw-loss gradient)
+        T.inverse_lbs_backward(pbw, A, tpts, d_tpts, d_pbw, True)
+        # posed blend-weight field (same parameters: gradients accumulate)
+        T.bw_softmax_backward(init_p, pbw, d_pbw, d_delta, None)
+        T.gemm([(Op(d_delta).T, Op(h8p).T)], gWfc, accumulate=True, split_k=sk)
+        T.colsum(d_delta, gbfc, accumulate=True)
+        dz = T.gemm([(Op(d_delta), Op(Wfc).T)], e(m, 256), relu_mask=h8p)
+        trunk_p.backward(dz, g_bw_lat[latent_index + 1:latent_index + 2], None)
+
+        selb = sel.bool()
+        ret = {'rgb_map': rgb_map.view(1, R, 3), 'acc_map': acc_map.view(1, R), 'depth_map': depth_map.view(1, R), 'raw': raw.view(1, n, 4),
+               'pbw': pbw[selb].view(1, -1, 24), 'tbw': tbw[selb].view(1, -1, 24)}
+        stats = {'bw_loss': losses[0], 'img_loss': losses[1], 'loss': losses[0] + losses[1]}
+        self._keep = (keep, o, d, near, far, tr, A, pvol, tvol, pb, tb, rgb_gt, mask)
+        return ret, stats, G
+
+
+class _LossFn(torch.autograd.Function):
+    """Carries the kernel-computed gradients into torch.autograd: loss.backward() adds g * dloss/dparam to param.grad."""
+
+    @staticmethod
+    def forward(ctx, loss, flat_grad, *params):
+        ctx.flat = flat_grad
+        ctx.shapes = [p.shape for p in params]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        out, off = [], 0
+        for s in ctx.shapes:
+            k = 1
+            for v in s:
+                k *= v
+            out.append((ctx.flat[off:off + k] * g).view(s))
+            off += k
+        return (None, None, *out)
+
+
+class NetworkWrapper(nn.Module):
+    """tpose_trainer.NetworkWrapper: forward(batch) -> (ret, loss, scalar_stats, image_stats)."""
+
+    def __init__(self, net, cfg=None):
+        super().__init__()
+        self.net = net
+        self.cfg = cfg if cfg is not None else getattr(net, 'cfg', None) or config.global_cfg()
+        self.renderer = Renderer(net, self.cfg)
+        self.__dict__['_step'] = TrainStep(net, self.cfg)
+
+    def forward(self, batch, t_rand=None):
+        cfg = self.cfg
+        if t_rand is None and config.get(cfg, 'perturb') > 0. and self.net.training:
+            R = batch['ray_o'].shape[1]
+            t_rand = torch.rand(1, R, int(config.get(cfg, 'N_samples')))       # CPU generator, as tpose_renderer.py:35
+        ret, stats, G = self.__dict__['_step'].run(batch, t_rand)
+        params = [p for _, p in self.net.named_parameters()]
+        loss = _LossFn.apply(stats['loss'], G.flat, *params)
+        scalar_stats = {'bw_loss': stats['bw_loss'], 'img_loss': stats['img_loss'], 'loss': loss}
+        return ret, loss, scalar_stats, {}
+
+
+def allreduce_gradients(net, world_size: int, group=None):
+    """Data-parallel gradient average (what DistributedDataParallel does in trainer.py:13-19) as ONE collective over a flat
+    buffer: NCCL all-reduce(sum) of 1 274 652 floats, then 1/world."""
+    import torch.distributed as dist
+    params = [p for p in net.parameters() if p.grad is not None]
+    if world_size <= 1 or not params:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, group=group)
+    flat.mul_(1.0 / world_size)
+    off = 0
+    for p in params:
+        k = p.numel()
+        p.grad.copy_(flat[off:off + k].view_as(p.grad))
+        off += k
+
+
+def train_iteration(wrapper: NetworkWrapper, batch, optimizer, world_size: int = 1, t_rand=None, clip: float = 40.0):
+    """One iteration of Trainer.train (trainer.py:62-66): zero_grad, forward, backward, [allreduce], clip_grad_value_, step."""
+    optimizer.zero_grad()
+    ret, loss, stats, _ = wrapper(batch, t_rand=t_rand)
+    loss.mean().backward()
+    allreduce_gradients(wrapper.net, world_size)
+    torch.nn.utils.clip_grad_value_(wrapper.net.parameters(), clip)
+    optimizer.step()
+    return ret, stats

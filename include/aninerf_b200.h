@@ -265,6 +265,88 @@ int aninerf_query_alpha(aninerf_net *net, const aninerf_frame *frame_host, const
                         void *stream);
 int64_t aninerf_query_workspace_bytes(int64_t n, int64_t pbw_voxels);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step: tpose_trainer.NetworkWrapper.forward (lib/train/trainers/tpose_trainer.py:21-73) and the
+ * backward pass torch.autograd derives for it in the reference (Trainer.train, trainer.py:62-66).
+ * The Python mirror (animatable_nerf_b200/tpose_trainer.py) chains these entries layer by layer and
+ * keeps every activation in fp32.
+ * ---------------------------------------------------------------------------------------- */
+
+/* The front end of the fused path alone: stratified samples (+jitter) -> pose space -> pnorm < norm_th mask ->
+ * per-2048-ray-chunk argmin forcing -> stable compaction (tpose_renderer.py:14-69, tpose_nerf_network.py:143-157).
+ * index (n',) flat sample index; ppts, viewdir (n',3); dists (n',); z_vals (n_rays,S) or NULL; buffers sized n_rays*S. */
+int64_t aninerf_front_end_workspace_bytes(int64_t n_rays, int32_t n_samples, int64_t pbw_voxels);
+int aninerf_front_end(const aninerf_frame *frame_host, const aninerf_render_params *params_host, const float *ray_o, const float *ray_d,
+                      const float *near, const float *far, const float *t_vals, const float *t_rand, int64_t n_rays, int32_t *index,
+                      float *ppts, float *viewdir, float *dists, float *z_vals, int32_t *n_active, int32_t *chunk_offsets,
+                      void *workspace, int64_t workspace_bytes, void *stream);
+
+/* One dense product on the tcgen05 tensor cores, fp32 in / fp32 out, every product as bf16x3 (fp32-equivalent):
+ *     C[M,N] = epilogue( sum_s A_s[M,K_s] * B_s[N,K_s]^T )
+ * It replaces F.conv1d (kernel 1) forward, its data gradient and its weight gradient (tpose_nerf_network.py:68-72,
+ * 256-274 and their autograd).  Operand element (row r, k) of segment s is ptr[r*row_stride + k*k_stride], so X, X^T, W, W^T
+ * and column ranges of W are read in place; two segments give the skip / view layers' concatenated inputs.
+ * epilogue: + bias[n]; + C (accumulate); ReLU; * (relu_mask[m,n] > 0).  split_k > 1 (one segment, plain epilogue):
+ * the K range is split over CTAs into `workspace` and reduced in fixed order (deterministic weight gradients). */
+typedef struct {
+  const float *A;
+  int64_t a_row_stride, a_k_stride;
+  const float *B;
+  int64_t b_row_stride, b_k_stride;
+  int32_t K;
+} aninerf_gemm_seg;
+typedef struct {
+  aninerf_gemm_seg seg[2];
+  int32_t n_seg, M, N;
+  float *C;
+  int64_t ldc;
+  const float *bias;
+  const float *relu_mask;
+  int64_t ld_mask;
+  int32_t relu, accumulate, split_k;
+} aninerf_gemm;
+int64_t aninerf_gemm_workspace_bytes(const aninerf_gemm *g_host);
+int aninerf_gemm_x3(const aninerf_gemm *g_host, void *workspace, int64_t workspace_bytes, void *stream);
+/* out[n] (+)= sum_m X[m*ld + n] (bias gradients), fixed summation order; workspace >= ceil(M/256)*N floats. */
+int aninerf_colsum(const float *X, int64_t ld, int64_t M, int32_t N, float *out, int32_t accumulate, void *workspace,
+                   int64_t workspace_bytes, void *stream);
+
+/* Positional encoding (lib/networks/embedder.py:11-36) as a stand-alone op and its gradient w.r.t. x. out/d_pe rows have
+ * leading dimension ld >= 3 + 6*n_freq. */
+int aninerf_pe_forward(const float *x, int64_t n, int32_t n_freq, float *out, int64_t ld, void *stream);
+int aninerf_pe_backward(const float *x, const float *d_pe, int64_t ld, int64_t n, int32_t n_freq, float *d_x, int32_t accumulate,
+                        void *stream);
+/* bw = softmax(log(init + 1e-9) + delta) over the 24 bones (tpose_nerf_network.py:74-76); init rows have leading dimension
+ * ld_init (25 for the sampled volume rows).  Backward: d_delta (n,24) and, when non-NULL, d_init (n,24). */
+int aninerf_bw_softmax_forward(const float *init, int64_t ld_init, const float *delta, int64_t n, float *bw, void *stream);
+int aninerf_bw_softmax_backward(const float *init, int64_t ld_init, const float *bw, const float *d_bw, int64_t n, float *d_delta,
+                                float *d_init, void *stream);
+/* Gradient of pose_points_to_tpose_points (blend_utils.py:41-59) w.r.t. the blend weights. */
+int aninerf_inverse_lbs_backward(const float *bw, const float *A, const float *tpts, const float *d_tpts, int64_t n, float *d_bw,
+                                 int32_t accumulate, void *stream);
+/* Gradient of pts_sample_blend_weights (blend_utils.py:119-149) w.r.t. the query points, first 24 channels
+ * (grid_sampler_3d_backward, align_corners, border padding).  d_out (n,24). */
+int aninerf_sample_blend_weights_backward(const float *pts, int64_t n, const float *vol, const int32_t dims_host[3], const float *bounds,
+                                          const float *d_out, float *d_pts, int32_t accumulate, void *stream);
+/* Tail of Network.forward (tpose_nerf_network.py:186-212) and its backward.  raw_full (n_total,4) pre-zeroed. */
+int aninerf_nerf_tail_forward(const float *sigma, const float *rgb, const float *tpts, const float *tbounds, const float *dists,
+                              const int32_t *index, int64_t n, float *raw_full, float *sigma_masked, void *stream);
+int aninerf_nerf_tail_backward(const float *d_raw_full, const float *raw_full, const int32_t *index, const float *sigma_masked,
+                               const float *tpts, const float *tbounds, const float *dists, int64_t n, float *d_sigma, float *d_rgb,
+                               void *stream);
+/* Backward of raw2outputs (nerf_net_utils.py:6-36) for a gradient arriving on rgb_map. d_raw (n_rays,S,4). */
+int aninerf_composite_backward(const float *raw, const float *d_rgb_map, int64_t n_rays, int32_t n_samples, int32_t white_bkgd,
+                               float *d_raw, void *stream);
+/* img_loss = mean((rgb_map[mask] - rgb[mask])^2) and its gradient (tpose_trainer.py:60-63). loss: device float. */
+int aninerf_img_loss(const float *rgb_map, const float *rgb_gt, const uint8_t *mask, int64_t n_rays, float *loss, float *d_rgb_map,
+                     void *stream);
+/* alpha_ind of tpose_nerf_network.py:192-194 for every chunk: sigma_masked > train_th plus the chunk's first arg-max row. */
+int aninerf_select_rows(const float *sigma_masked, const int32_t *chunk_offsets, int32_t n_chunks, float train_th, uint8_t *sel,
+                        int32_t *n_sel, void *stream);
+/* bw_loss = smooth_l1(pbw[sel], tbw[sel]) (tpose_trainer.py:48-51) and its gradients (n,24), zero on unselected rows. */
+int aninerf_bw_loss(const float *pbw, const float *tbw, const uint8_t *sel, const int32_t *n_sel, int64_t n, float *loss, float *d_pbw,
+                    float *d_tbw, void *stream);
+
 /* Optional per-stage device timing of aninerf_render_rays (CUDA events on the launching stream).
  * Stage order: split volumes, clear raw, mask+scan+compact front end, (unused), (unused), blend-weight
  * field at posed points (+LBS), blend-weight field at canonical points, NeRF field (+tail), compositing.
