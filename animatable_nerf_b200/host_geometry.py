@@ -83,3 +83,43 @@ def look_at_camera(center: np.ndarray, distance: float, azimuth: float = 0.0, up
     R = np.stack([right, down, fwd])            # rows = camera axes in world coords
     T = -R @ pos
     return R, T.reshape(3, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# novel-view camera path (lib/utils/render_utils.py:11-28, 77-127 `gen_path`)
+# ---------------------------------------------------------------------------------------------
+def _unit(v):
+    return v / np.linalg.norm(v)
+
+
+def circular_camera_path(RT, render_views: int, center=None):
+    """World->camera matrices of a `render_views`-step circular sweep around the capture rig, from the rig's
+    world->camera matrices `RT` (c,4,4): the path render_utils.gen_path builds for `tpose_novel_view_dataset`.
+    Camera axes follow the LLFF convention used there ([down, right, backwards]); the path is an ellipse whose radii
+    are 1.3 x the 80th percentile of the rig cameras' offsets in the mean camera frame.  Host, float64, once per sweep."""
+    c2w_all = np.linalg.inv(np.array(RT, dtype=np.float64))
+    c2w_all = np.concatenate([c2w_all[:, :, 1:2], c2w_all[:, :, 0:1], -c2w_all[:, :, 2:3], c2w_all[:, :, 3:4]], 2)
+    up = _unit(c2w_all[:, :3, 0].sum(0))
+    gaze = _unit(c2w_all[0, :3, 2])
+    side = _unit(np.cross(gaze, up))
+    fwd = _unit(np.cross(up, side))
+    z_off = 0
+    if center is None:
+        center = c2w_all[:, :3, 3].mean(0)
+        z_off = 1.3
+    frame = np.stack([up, side, fwd, center], 1)                                   # (3,4) mean camera -> world
+    local = np.matmul(frame[:3, :3].T, (c2w_all[:, :3, 3] - frame[:3, 3])[..., np.newaxis])[..., 0].T
+    rads = np.percentile(np.abs(local), 80, -1) * 1.3
+    rads = np.array(list(rads) + [1.])
+    target = np.dot(frame[:3, :4], np.array([z_off, 0, 0, 1.]))
+    out = []
+    for theta in np.linspace(0., 2 * np.pi, render_views + 1)[:-1]:
+        pos = np.dot(frame[:3, :4], np.array([0, np.sin(theta), np.cos(theta), 1] * rads))
+        z = _unit(pos - target)
+        v1 = _unit(np.cross(z, up))
+        v0 = _unit(np.cross(v1, z))
+        m = np.stack([v0, v1, z, pos], 1)
+        m = np.concatenate([m[:, 1:2], m[:, 0:1], -m[:, 2:3], m[:, 3:4]], 1)
+        m = np.concatenate([m, np.array([[0., 0., 0., 1.]])], 0)
+        out.append(np.linalg.inv(m))
+    return out

@@ -118,6 +118,15 @@ def make_camera(frame: dict, H: int = 1024, W: int = 1024, focal: float = 1070.0
     return K, R, T
 
 
+def make_camera_rig(frame: dict, n_views: int = 4, distance: float = 3.0):
+    """World->camera matrices (n_views,4,4) float64 of a ring of cameras around the body (the capture rig of a sweep)."""
+    rig = np.zeros((n_views, 4, 4))
+    for i in range(n_views):
+        _, R, T = make_camera(frame, 64, 64, distance=distance, azimuth=2 * np.pi * i / n_views)
+        rig[i, :3, :3], rig[i, :3, 3], rig[i, 3, 3] = R, np.asarray(T).ravel(), 1.0
+    return rig
+
+
 FRAME_KEYS = ('A', 'R', 'Th', 'pbw', 'tbw', 'pbounds', 'wbounds', 'tbounds', 'latent_index', 'bw_latent_index')
 
 

@@ -71,10 +71,11 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.windows = []          # (t0, t1) of the timed regions: only samples taken under load are reported
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -82,7 +83,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if self.proc is None:
@@ -91,7 +92,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in self.windows)]
+        if not inside:             # region shorter than the sampling period: take the samples around it
+            inside = [r for t, r in self.rows if any(a - 0.1 <= t <= b + 0.1 for a, b in self.windows)] or [r for _, r in self.rows]
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -222,6 +226,104 @@ def stage_kernel_rooflines(dev, frame, hbm_gbs, ray_pts=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# the other BASELINE configs, measured briefly next to the headline (parity for each is in tests/)
+# ------------------------------------------------------------------------------------------------
+def _time_ms(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def other_configs(dev, frame, rank, world):
+    """BASELINE configs 3-5 on this rank's share: novel-pose 1000x1000 render (s9p shapes), one training iteration of
+    1024 rays x 64 samples per GPU (+ flat-gradient allreduce), 256^3 density grid and a novel-view sweep.
+    Device times (CUDA events), inputs resident."""
+    import torch.distributed as dist
+    from animatable_nerf_b200 import config, frontend, host_geometry, ray_tiles, sweep, synthetic
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer import Renderer
+    from animatable_nerf_b200.tpose_trainer import NetworkWrapper, train_iteration
+    out = {}
+    # ---- config 3: aninerf_s9p novel pose with the neural blend-weight field of stage 2, 1000x1000, ray-tiled --------
+    K, R, T = synthetic.make_camera(frame, 1000, 1000, focal=1150.0)
+    ro, rd, near, far, _ = frontend.get_rays_within_bounds(1000, 1000, K, R, T, frame['wbounds'], device=dev)
+    cfg3 = config.make_cfg(perturb=0., b200_render_only=True, aninerf_animation=True, test_novel_pose=True, num_train_frame=260, num_eval_frame=133)
+    net3 = Network(cfg3)
+    net3.load_state_dict(synthetic.make_state_dict(seed=1, num_train_frame=260, num_eval_frame=133))
+    net3 = net3.to(dev).eval()
+    r3 = Renderer(net3, cfg3)
+    full3 = synthetic.make_render_batch(frame, ro, rd, near, far, device=dev)
+    full3['bw_latent_index'] = torch.tensor([7], device=dev)
+    mine3 = ray_tiles.shard_batch(full3, rank, world)
+    n3 = ro.shape[0]
+
+    def step3():
+        o = r3.render_device(mine3, want_bw=False)
+        maps = torch.cat([o['rgb_map'], o['acc_map'][:, None], o['depth_map'][:, None]], dim=1)
+        return ray_tiles.gather_maps(maps, n3, rank, world)
+    ms = _time_ms(step3)
+    out['config3_novel_pose_1000x1000'] = {'ms_per_frame': ms, 'samples_per_s': n3 * 64 / (ms * 1e-3), 'rays_in_box': n3,
+                                           'fields': 'novel_pose_bw (num_eval_frame 133) + NeRF (num_train_frame 260)'}
+    del r3, net3, full3, mine3
+    # ---- config 4: training iteration, 1024 rays x 64 per GPU, data-parallel gradient allreduce -----------------------
+    K, R, T = synthetic.make_camera(frame, 1024, 1024)
+    ro, rd, near, far, _ = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    cfg4 = config.make_cfg(perturb=1.)
+    net4 = Network(cfg4)
+    net4.load_state_dict(synthetic.make_state_dict(seed=0))
+    net4 = net4.to(dev).train()
+    w4 = NetworkWrapper(net4, cfg4)
+    tb, t_rand = synthetic.make_train_batch(frame, ro.cpu().numpy(), rd.cpu().numpy(), near.cpu().numpy(), far.cpu().numpy(), n_rays=1024,
+                                            ray_seed=3 + rank, device=dev)
+    opt = torch.optim.Adam(net4.parameters(), lr=5e-4)
+    L = None
+    from animatable_nerf_b200 import _lib
+    L = _lib.lib()
+    c0 = L.aninerf_launch_count()
+    ms = _time_ms(lambda: train_iteration(w4, tb, opt, world_size=world, t_rand=t_rand), reps=5, warm=2)
+    launches = (L.aninerf_launch_count() - c0) / 7
+    out['config4_train_step_1024x64_per_gpu'] = {'ms_per_iteration': ms, 'samples_per_s': world * 1024 * 64 / (ms * 1e-3),
+                                                 'iterations_per_s': 1e3 / ms, 'kernel_launches_per_iteration': launches,
+                                                 'includes': 'forward + backward + flat-gradient allreduce + clip + Adam',
+                                                 'precision': 'fp32 activations, bf16x3 tensor-core products'}
+    del w4, net4, opt
+    # ---- config 5: 256^3 density grid (chunks of 131072 points round-robin) + novel-view sweep (views round-robin) ------
+    cfg5 = config.make_cfg(perturb=0., b200_render_only=True)
+    net5 = Network(cfg5)
+    net5.load_state_dict(synthetic.make_state_dict(seed=0))
+    net5 = net5.to(dev).eval()
+    fb = synthetic.collate_frame(frame, dev)
+    wb = np.asarray(frame['wbounds'], dtype=np.float64)
+    vs = ((wb[1] - wb[0]) / 255.0).tolist()
+    pts = sweep.grid_points(frame['wbounds'], vs, dev)[:256, :256, :256].contiguous()
+    ms = _time_ms(lambda: sweep.query_density_grid(net5, fb, pts, None, rank, world), reps=2, warm=1)
+    out['config5_density_grid_256^3'] = {'ms': ms, 'points_per_s': pts.shape[0] * pts.shape[1] * pts.shape[2] / (ms * 1e-3),
+                                         'grid': list(pts.shape[:3])}
+    rig = synthetic.make_camera_rig(frame, n_views=8)
+    n_views = 8 * world
+    path = host_geometry.circular_camera_path(list(rig), n_views)
+    K5 = np.array([[1070., 0, 512.], [0, 1070., 512.], [0, 0, 1.]])
+    r5 = Renderer(net5, cfg5)
+
+    def sweep_step():
+        loc = sweep.render_views(r5, fb, K5, path, 1024, 1024, rank, world)
+        return sweep.gather_views(loc, n_views, 1024, 1024, rank, world, dev)
+    ms = _time_ms(sweep_step, reps=2, warm=1)
+    out['config5_view_sweep_1024x1024'] = {'views': n_views, 'ms_per_sweep': ms, 'ms_per_view': ms / n_views, 'views_per_s': n_views / (ms * 1e-3),
+                                           'includes': 'on-device ray generation + box intersection + compaction, render, image gather'}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -283,6 +385,7 @@ def run_b200(args):
         evs = []
         L.aninerf_profile_enable(1 if profile else 0)
         barrier()
+        t_begin = time.time()
         for _ in range(steps):
             flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,6 +395,7 @@ def run_b200(args):
             evs.append((a, b))
             del r
         barrier()
+        clocks.windows.append((t_begin, time.time()))
         L.aninerf_profile_enable(0)
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -299,6 +403,11 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML init over every GPU of the box) stalls
+    # kernel launches for tens of milliseconds and must not land in the timed region
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         out, _ = step_device()
         step_e2e()
@@ -319,9 +428,6 @@ def run_b200(args):
     import ctypes as C
     ms_buf, calls_buf = (C.c_double * 9)(), (C.c_int64 * 9)()
     L.aninerf_profile_read(ms_buf, calls_buf, 1)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     launches0 = L.aninerf_launch_count()
     total_ms = timed(lambda: step_device(), args.steps, profile=True)
     launches = L.aninerf_launch_count() - launches0
@@ -383,6 +489,12 @@ def run_b200(args):
         line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
                                 'sample': f'oracle/ port of Renderer.render, {CPU_SAMPLE_RAYS} rays x 64 samples of the same frame, '
                                           f'torch {torch.__version__} CPU, median of 3 ({sec:.2f} s each)'}
+    if not args.no_extra:
+        try:
+            extra = other_configs(dev, frame, rank, world)
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            extra = {'error': repr(e)}
+        line['other_configs'] = extra
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -398,6 +510,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extra', action='store_true', help='skip the short runs of BASELINE configs 3-5')
     args = ap.parse_args()
     return run_reference(args) if args.impl == 'reference' else run_b200(args)
 

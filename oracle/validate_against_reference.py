@@ -186,6 +186,16 @@ def main():
                         RT=mb['RT'][0].numpy(), H=int(mb['H']), W=int(mb['W']), inside=out_om['_debug']['inside'].numpy(),
                         **{k: out_rm[k].numpy() for k in mkeys})
 
+    # ---------------- novel-view camera path (render_utils.gen_path) ------------------------------
+    if ref.render_utils is not None:
+        from animatable_nerf_b200 import host_geometry
+        rig = [m.astype(np.float64) for m in mb['RT'][0].numpy()]
+        cfg.render_views = 16
+        path_r = np.array(ref.render_utils.gen_path([m.copy() for m in rig]))
+        path_o = np.array(host_geometry.circular_camera_path([m.copy() for m in rig], 16))
+        report('gen_path (16-view circular sweep)', 'render_utils.py:77-127', path_r.shape == path_o.shape and float(np.abs(path_r - path_o).max()) < 1e-12,
+               f'max abs diff {float(np.abs(path_r - path_o).max()):.1e} (float64 host code)')
+
     # ---------------- training step (tpose_trainer.NetworkWrapper + Trainer.train up to the optimizer) ---------
     if ref.trainer_mod is not None:
         tb, t_rand = synthetic.make_train_batch(small, ray_o, ray_d, near, far, n_rays=512)

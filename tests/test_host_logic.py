@@ -122,3 +122,31 @@ def test_synthetic_batch_schema():
     assert b['latent_index'].dtype == torch.int64
     # skinning weights in the volumes are convex combinations
     assert torch.allclose(b['pbw'][..., :24].sum(-1), torch.ones_like(b['pbw'][..., 0]), atol=1e-5)
+
+
+def test_sweep_and_grid_sharding_cover_every_unit_once():
+    from animatable_nerf_b200 import sweep
+    for n_views, world in ((64, 8), (50, 4), (3, 8), (1, 1)):
+        got = sorted(v for r in range(world) for v in sweep.views_of_rank(n_views, r, world))
+        assert got == list(range(n_views))
+    for n_pts, world in ((256 ** 3, 8), (131072 * 3 + 17, 2), (5, 4)):
+        cs = [sweep.chunks_of_rank(n_pts, r, world) for r in range(world)]
+        flat = sorted(c for x in cs for c in x)
+        assert flat == list(range((n_pts + sweep.GRID_CHUNK - 1) // sweep.GRID_CHUNK))
+        assert max(len(x) for x in cs) - min(len(x) for x in cs) <= 1
+
+
+def test_circular_camera_path_is_a_closed_orbit_of_rigid_transforms():
+    import numpy as np
+    from animatable_nerf_b200 import host_geometry, synthetic
+    frame = synthetic.make_frame(voxel=0.1)
+    _, _, RT = synthetic.make_silhouettes(frame, n_views=6, H=64, W=64, focal=66.0)
+    path = host_geometry.circular_camera_path(list(RT.astype(np.float64)), 16)
+    assert len(path) == 16
+    centre = np.mean([np.linalg.inv(m)[:3, 3] for m in path], axis=0)
+    for m in path:
+        assert m.shape == (4, 4)
+        assert np.allclose(m[:3, :3] @ m[:3, :3].T, np.eye(3), atol=1e-9) and abs(np.linalg.det(m[:3, :3]) - 1) < 1e-9
+        pos = np.linalg.inv(m)[:3, 3]
+        look = np.linalg.inv(m)[:3, 2]                    # camera z axis in the world
+        assert np.dot(look, centre - pos) > 0               # every camera looks towards the orbit's inside
