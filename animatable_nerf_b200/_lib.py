@@ -51,6 +51,10 @@ class RenderOutputs(C.Structure):
                 ('n_active', C.c_void_p), ('chunk_offsets', C.c_void_p)]
 
 
+class PeerGather(C.Structure):
+    _fields_ = [('maps', C.c_void_p * 8), ('world', C.c_int32), ('rank', C.c_int32)]
+
+
 class Silhouettes(C.Structure):
     _fields_ = [('msks', C.c_void_p), ('Ks', C.c_void_p), ('RT', C.c_void_p), ('n_views', C.c_int32), ('H', C.c_int32), ('W', C.c_int32)]
 
@@ -95,6 +99,8 @@ PROTOTYPES = {
                                    C.POINTER(RenderOutputs), _VP, _I64, _VP]),
     'aninerf_render_rays_culled': (_I32, [_VP, C.POINTER(Frame), C.POINTER(RenderParams), C.POINTER(Silhouettes), _VP, _VP, _VP, _VP, _VP,
                                           _VP, _I64, C.POINTER(RenderOutputs), _VP, _I64, _VP]),
+    'aninerf_render_rays_tiled': (_I32, [_VP, C.POINTER(Frame), C.POINTER(RenderParams), C.POINTER(Silhouettes), C.POINTER(PeerGather), _VP, _VP, _VP,
+                                         _VP, _VP, _VP, _I64, C.POINTER(RenderOutputs), _VP, _I64, _VP]),
     'aninerf_inside_all_views': (_I32, [_VP, _I64, C.POINTER(Silhouettes), _VP, _VP]),
     'aninerf_front_end_workspace_bytes': (_I64, [_I64, _I32, _I64]),
     'aninerf_front_end': (_I32, [C.POINTER(Frame), C.POINTER(RenderParams), _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP,

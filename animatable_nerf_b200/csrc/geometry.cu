@@ -336,13 +336,21 @@ __global__ void __launch_bounds__(256) lbs_kernel(const float *__restrict__ pts,
 // 8. alpha compositing (nerf_net_utils.py:6-36): one warp per ray, S/32 samples per lane,
 //    exclusive product scan of (1 - alpha + 1e-10) with shuffles.
 // =============================================================================================
+// Fused compositing + image gather over NVLink peer memory: when peers.world > 0 the ray's (rgb, acc, depth) row is stored
+// straight into EVERY rank's frame-ordered image buffer (peer-mapped symmetric memory), 20 B per ray and peer, instead of
+// an all_gather + reorder afterwards.  Local ray r belongs to local chunk r / chunk_rays = global chunk i*world + rank.
+struct PeerScatter {
+  float *maps[ANINERF_MAX_PEERS];
+  int world, rank, chunk_rays;
+};
+
 template <int SPL>   // samples per lane (S = 32*SPL), lane owns samples [lane*SPL, lane*SPL+SPL)
 __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict__ raw, const float *__restrict__ z_vals,
                                                         const float *__restrict__ near, const float *__restrict__ far,
                                                         const float *__restrict__ t_vals, int64_t n_rays, int white_bkgd,
                                                         float *__restrict__ rgb_map, float *__restrict__ acc_map,
                                                         float *__restrict__ depth_map, float *__restrict__ disp_map,
-                                                        float *__restrict__ weights) {
+                                                        float *__restrict__ weights, PeerScatter peers) {
   constexpr int S = 32 * SPL;
   int lane = threadIdx.x & 31;
   int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -412,6 +420,18 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
     if (acc_map) acc_map[ray] = acc;
     if (depth_map) depth_map[ray] = dep;
     if (disp_map) disp_map[ray] = 1.0f / fmaxf(1e-10f, dep / acc);
+    if (peers.world > 0) {
+      const int64_t lc = ray / peers.chunk_rays;
+      const int64_t row = (lc * peers.world + peers.rank) * peers.chunk_rays + (ray - lc * peers.chunk_rays);
+      for (int k = 0; k < peers.world; ++k) {
+        float *dst = peers.maps[k] + row * 5;
+        dst[0] = r;
+        dst[1] = g;
+        dst[2] = b;
+        dst[3] = acc;
+        dst[4] = dep;
+      }
+    }
   }
 }
 
@@ -918,10 +938,10 @@ int aninerf_composite(const float *raw, const float *z_vals, int64_t n_rays, int
   cudaStream_t st = (cudaStream_t)stream;
   if (S == 64)
     composite_kernel<2><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, nullptr, nullptr, nullptr, n_rays, white_bkgd, rgb_map,
-                                                acc_map, depth_map, disp_map, weights);
+                                                acc_map, depth_map, disp_map, weights, PeerScatter{});
   else
     composite_kernel<1><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, nullptr, nullptr, nullptr, n_rays, white_bkgd, rgb_map,
-                                                acc_map, depth_map, disp_map, weights);
+                                                acc_map, depth_map, disp_map, weights, PeerScatter{});
   ANI_LAUNCHED();
   return ANINERF_OK;
 }
@@ -984,14 +1004,22 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
 }
 
 int launch_composite_fused(const float *raw, const float *near, const float *far, const float *t_vals, const float *z_vals, int64_t n_rays,
-                           int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, cudaStream_t st) {
+                           int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, const aninerf_peer_gather *peers,
+                           int chunk_rays, cudaStream_t st) {
   unsigned blocks = (unsigned)((n_rays + 7) / 8);
+  PeerScatter ps{};
+  if (peers) {
+    ps.world = peers->world;
+    ps.rank = peers->rank;
+    ps.chunk_rays = chunk_rays;
+    for (int k = 0; k < peers->world; ++k) ps.maps[k] = (float *)peers->maps[k];
+  }
   if (S == 64)
     composite_kernel<2><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, near, far, t_vals, n_rays, white_bkgd, rgb_map, acc_map,
-                                                depth_map, nullptr, nullptr);
+                                                depth_map, nullptr, nullptr, ps);
   else
     composite_kernel<1><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, near, far, t_vals, n_rays, white_bkgd, rgb_map, acc_map,
-                                                depth_map, nullptr, nullptr);
+                                                depth_map, nullptr, nullptr, ps);
   ANI_LAUNCHED();
   return ANINERF_OK;
 }

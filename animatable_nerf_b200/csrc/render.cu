@@ -21,7 +21,8 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
                      int32_t *index, float *ppts, float *viewdir, float *dists, int32_t *n_active, int32_t *chunk_offsets,
                      const aninerf_silhouettes *sil, cudaStream_t st);
 int launch_composite_fused(const float *raw, const float *near, const float *far, const float *t_vals, const float *z_vals, int64_t n_rays,
-                           int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, cudaStream_t st);
+                           int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, const aninerf_peer_gather *peers,
+                           int chunk_rays, cudaStream_t st);
 int launch_mask_points(const float *wpts, int64_t n, const float *R, const float *Th, const float *bounds, const int32_t dims[3],
                        const float *dist_plane, float norm_th, int64_t chunk_pts, uint8_t *mask, unsigned long long *chunk_argmin,
                        float *ppts, cudaStream_t st);
@@ -118,8 +119,8 @@ static int64_t carve_render(Carver &c, int64_t n_rays, int S, int want_bw, int64
 using namespace aninerf;
 
 static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
-                            const float *ray_o, const float *ray_d, const float *near, const float *far, const float *t_vals,
-                            const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
+                            const aninerf_peer_gather *peers, const float *ray_o, const float *ray_d, const float *near, const float *far,
+                            const float *t_vals, const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
                             int64_t workspace_bytes, void *stream);
 
 extern "C" {
@@ -133,7 +134,7 @@ int64_t aninerf_render_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_
 int aninerf_render_rays(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const float *ray_o, const float *ray_d,
                         const float *near, const float *far, const float *t_vals, const float *t_rand, int64_t n_rays,
                         const aninerf_render_outputs *out, void *workspace, int64_t workspace_bytes, void *stream) {
-  return render_rays_impl(net, fr, pr, nullptr, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
+  return render_rays_impl(net, fr, pr, nullptr, nullptr, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
 }
 
 int aninerf_render_rays_culled(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
@@ -142,14 +143,29 @@ int aninerf_render_rays_culled(aninerf_net *net, const aninerf_frame *fr, const 
                                int64_t workspace_bytes, void *stream) {
   ANI_CHECK_ARG(sil && sil->msks && sil->Ks && sil->RT && sil->n_views > 0 && sil->H > 0 && sil->W > 0);
   ANI_CHECK_ARG(pr && !pr->want_bw);
-  return render_rays_impl(net, fr, pr, sil, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
+  return render_rays_impl(net, fr, pr, sil, nullptr, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
+}
+
+int aninerf_render_rays_tiled(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
+                              const aninerf_peer_gather *peers, const float *ray_o, const float *ray_d, const float *near, const float *far,
+                              const float *t_vals, const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
+                              int64_t workspace_bytes, void *stream) {
+  if (sil) {
+    ANI_CHECK_ARG(sil->msks && sil->Ks && sil->RT && sil->n_views > 0 && sil->H > 0 && sil->W > 0);
+    ANI_CHECK_ARG(pr && !pr->want_bw);
+  }
+  if (peers) {
+    ANI_CHECK_ARG(peers->world >= 1 && peers->world <= ANINERF_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
+    for (int k = 0; k < peers->world; ++k) ANI_CHECK_ARG(peers->maps[k] != nullptr);
+  }
+  return render_rays_impl(net, fr, pr, sil, peers, ray_o, ray_d, near, far, t_vals, t_rand, n_rays, out, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"
 
 static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const aninerf_render_params *pr, const aninerf_silhouettes *sil,
-                            const float *ray_o, const float *ray_d, const float *near, const float *far, const float *t_vals,
-                            const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
+                            const aninerf_peer_gather *peers, const float *ray_o, const float *ray_d, const float *near, const float *far,
+                            const float *t_vals, const float *t_rand, int64_t n_rays, const aninerf_render_outputs *out, void *workspace,
                             int64_t workspace_bytes, void *stream) {
   ANI_CHECK_ARG(net && fr && pr && out && ray_o && ray_d && near && far && t_vals && workspace && n_rays >= 0);
   ANI_CHECK_ARG(fr->A && fr->R && fr->Th && fr->pbw && fr->pbounds && fr->tbounds);
@@ -224,7 +240,8 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
     if ((rc = aninerf_sample_points(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, nullptr, s.z_vals, nullptr, stream))) return rc;
     z = s.z_vals;
   }
-  return launch_composite_fused(out->raw, near, far, t_vals, z, n_rays, S, pr->white_bkgd, out->rgb_map, out->acc_map, out->depth_map, st);
+  return launch_composite_fused(out->raw, near, far, t_vals, z, n_rays, S, pr->white_bkgd, out->rgb_map, out->acc_map, out->depth_map, peers,
+                                pr->chunk_rays, st);
 }
 
 extern "C" {

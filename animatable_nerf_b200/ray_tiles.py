@@ -78,3 +78,40 @@ def gather_maps(local: torch.Tensor, n_rays: int, rank: int, world: int, chunk: 
     recv = torch.empty(world * pad, C, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(recv, send, group=group)
     return recv.index_select(0, pos)
+
+
+class PeerImage:
+    """Frame image buffers in symmetric memory (every rank's buffer peer-mapped into every other rank over NVLink/NVSwitch)
+    for the fused compositing + gather of `aninerf_render_rays_tiled`: the compositing kernel of each rank stores its rays'
+    (rgb, acc, depth) rows into ALL ranks' buffers at their frame position, then ONE barrier makes the image complete
+    everywhere -- no all_gather, no reorder.  Two buffers alternate so that a rank may still read frame k while a faster
+    peer already writes frame k+1 (stream-ordered consumers; the barrier of frame k+1 orders everything else)."""
+
+    def __init__(self, capacity_rays: int, rank: int, world: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.rank, self.world, self.capacity = rank, world, int(capacity_rays)
+        group = group if group is not None else dist.group.WORLD
+        self.bufs = [symm.empty(self.capacity * 5, dtype=torch.float32, device=device) for _ in range(2)]
+        self.hdls = [symm.rendezvous(b, group) for b in self.bufs]
+        self.structs = []
+        for h in self.hdls:
+            pg = _lib.PeerGather()
+            ptrs = list(h.buffer_ptrs)
+            for k in range(world):
+                pg.maps[k] = ptrs[k]
+            pg.world, pg.rank = world, rank
+            self.structs.append(pg)
+        self.turn = 0
+
+    def begin(self):
+        """-> (PeerGather for render_device(peers=...), slot) of the next frame"""
+        slot = self.turn
+        self.turn ^= 1
+        return self.structs[slot], slot
+
+    def finish(self, slot: int, n_rays: int) -> torch.Tensor:
+        """Barrier across the ranks on the current stream, then the complete (n_rays, 5) image of this rank's buffer."""
+        assert n_rays <= self.capacity
+        self.hdls[slot].barrier(0, 10000)
+        return self.bufs[slot][:n_rays * 5].view(n_rays, 5)

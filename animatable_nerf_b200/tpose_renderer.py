@@ -56,10 +56,11 @@ class Renderer:
 
     # ---------------------------------------------------------------------------------------
     @torch.no_grad()
-    def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None):
+    def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None, peers=None):
         """The fused path, results left on the device.  Returns a dict with rgb_map/acc_map/depth_map
         (and raw, n_active, pbw_all/tbw_all/sigma_masked/chunk_offsets when want_bw).
-        silhouettes: (_lib.Silhouettes, keep-alive) from tpose_renderer_mmsk -- cull the samples first."""
+        silhouettes: (_lib.Silhouettes, keep-alive) from tpose_renderer_mmsk -- cull the samples first.
+        peers: _lib.PeerGather from ray_tiles.PeerImage -- the compositing kernel also stores the rows into every rank's image."""
         cfg = self.cfg
         ray_o, ray_d = batch['ray_o'], batch['ray_d']
         _lib.require_cuda(ray_o, "batch['ray_o']")
@@ -97,7 +98,12 @@ class Renderer:
         ws_bytes = _lib.lib().aninerf_render_workspace_bytes(R, S, int(want_bw), pv, tv)
         ws = self._workspace(ws_bytes, dev)
         tr = _lib.f32c(t_rand.reshape(R, S)) if t_rand is not None else None
-        if silhouettes is None:
+        if peers is not None:
+            _lib.check(_lib.lib().aninerf_render_rays_tiled(self.net.packed().handle, C.byref(fr), C.byref(pr),
+                                                            C.byref(silhouettes[0]) if silhouettes is not None else None, C.byref(peers),
+                                                            _lib.ptr(o), _lib.ptr(d), _lib.ptr(near), _lib.ptr(far), _lib.ptr(self._tv(S, dev)),
+                                                            _lib.ptr(tr), R, C.byref(ro), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+        elif silhouettes is None:
             _lib.check(_lib.lib().aninerf_render_rays(self.net.packed().handle, C.byref(fr), C.byref(pr), _lib.ptr(o), _lib.ptr(d),
                                                       _lib.ptr(near), _lib.ptr(far), _lib.ptr(self._tv(S, dev)), _lib.ptr(tr), R,
                                                       C.byref(ro), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))

@@ -368,18 +368,35 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        out = renderer.render_device(mine, want_bw=False)
+    # N > 1: the image gather is fused into the compositing kernel (stores into every rank's peer-mapped image over NVLink)
+    # followed by one symmetric-memory barrier; --gather nccl keeps the all_gather + reorder path for comparison
+    peer = None
+    if world > 1 and args.gather == 'peer':
+        try:
+            peer = ray_tiles.PeerImage(n_rays, rank, world, dev)
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f'bench: symmetric memory unavailable ({e!r}); using the NCCL all_gather path', file=sys.stderr)
+            peer = None
+
+    def render_and_gather(b):
+        if peer is not None:
+            pg, slot = peer.begin()
+            out = renderer.render_device(b, want_bw=False, peers=pg)
+            return out, peer.finish(slot, n_rays)
+        out = renderer.render_device(b, want_bw=False)
         maps = torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1)
-        img = ray_tiles.gather_maps(maps, n_rays, rank, world)
-        return out, img
+        return out, ray_tiles.gather_maps(maps, n_rays, rank, world)
+
+    def step_device():
+        return render_and_gather(mine)
 
     def step_e2e():
         b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
-        out = renderer.render_device(b, want_bw=False)
-        maps = torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1)
-        img = ray_tiles.gather_maps(maps, n_rays, rank, world)
-        return (img if rank == 0 else maps).to('cpu', non_blocking=False)
+        out, img = render_and_gather(b)
+        if rank == 0:
+            return img.to('cpu', non_blocking=False)
+        return torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1).to('cpu', non_blocking=False)
 
     def timed(fn, steps, profile=False):
         evs = []
@@ -462,6 +479,8 @@ def run_b200(args):
                    'precision': 'blend-weight MLP bf16x3 split (fp32-equivalent), NeRF MLP bf16, fp32 accumulate',
                    'mode': 'render-only (rgb/acc/depth; canonical tbw pass and raw/pbw/tbw outputs are training-contract outputs)',
                    'l2': 'flushed between timed steps (256 MiB fill)', 'parallelism': f'ray tiles: 2048-ray chunks round-robin over {world} GPU(s)',
+                   'gather': ('n/a (1 GPU)' if world == 1 else 'fused into the compositing kernel: stores into every rank\'s peer-mapped image over NVLink + 1 barrier'
+                              if peer is not None else 'NCCL all_gather + reorder'),
                    'weights': 'random init, seed 0, reference checkpoint layout'},
         'e2e': {'value': samples / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int((n_rays if rank == 0 else my_rays) * 20)},
@@ -510,6 +529,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='N>1 image gather: fused peer-memory stores (default) or NCCL all_gather')
     ap.add_argument('--no-extra', action='store_true', help='skip the short runs of BASELINE configs 3-5')
     args = ap.parse_args()
     return run_reference(args) if args.impl == 'reference' else run_b200(args)

@@ -31,6 +31,7 @@ extern "C" {
 #define ANINERF_N_BONES 24
 #define ANINERF_BW_CH 25          /* 24 skinning weights + distance-to-surface channel */
 #define ANINERF_MAX_SAMPLES 64    /* cfg.N_samples of every aninerf config (configs/aninerf_s9p.yaml:58) */
+#define ANINERF_MAX_PEERS 8       /* GPUs of one NVSwitch box */
 #define ANINERF_CHUNK_RAYS 2048   /* tpose_renderer.py:170 -- a semantic unit (per-chunk argmin forcing) */
 
 enum {
@@ -255,6 +256,22 @@ int aninerf_render_rays_culled(aninerf_net *net, const aninerf_frame *frame_host
                                const float *far, const float *t_vals, const float *t_rand, int64_t n_rays,
                                const aninerf_render_outputs *out_host, void *workspace, int64_t workspace_bytes,
                                void *stream);
+
+/* Ray-tiled multi-GPU render with the image gather FUSED into the compositing kernel: rank `rank` of `world` renders the
+ * 2048-ray chunks  rank, rank+world, ...  of the frame (its rays arrive concatenated in that order) and the compositing
+ * kernel stores every ray's (rgb, acc, depth) row -- 20 B -- straight into the frame-ordered (n_rays_frame, 5) image buffer
+ * of EVERY rank: maps[k] is rank k's buffer, peer-mapped over NVLink/NVSwitch (e.g. torch symmetric memory).  The caller
+ * follows the call with one cross-rank barrier; there is no all_gather and no reorder kernel.  sil_host / peers_host may be
+ * NULL (then this is aninerf_render_rays[_culled]). */
+typedef struct {
+  void *maps[ANINERF_MAX_PEERS];
+  int32_t world, rank;
+} aninerf_peer_gather;
+int aninerf_render_rays_tiled(aninerf_net *net, const aninerf_frame *frame_host, const aninerf_render_params *params_host,
+                              const aninerf_silhouettes *sil_host, const aninerf_peer_gather *peers_host, const float *ray_o,
+                              const float *ray_d, const float *near, const float *far, const float *t_vals, const float *t_rand,
+                              int64_t n_rays, const aninerf_render_outputs *out_host, void *workspace, int64_t workspace_bytes,
+                              void *stream);
 
 /* Network.calculate_alpha (= get_alpha), tpose_nerf_network.py:105-137: density-only query of
  * world points (norm_th hard-coded 0.1 by the reference -- passed in), processed in chunks of
