@@ -354,7 +354,11 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
   constexpr int S = 32 * SPL;
   int lane = threadIdx.x & 31;
   int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (ray >= n_rays) return;
+  const bool valid = ray < n_rays;
+  if (!valid) {
+    if (peers.world == 0) return;
+    ray = n_rays - 1;            // the peer scatter below needs the whole block at its __syncthreads: compute a dummy, write nothing
+  }
   float4 c[SPL];
   float z[SPL];
 #pragma unroll
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
 #pragma unroll
   for (int j = 0; j < SPL; ++j) {
     float w = c[j].w * T;
-    if (weights) weights[ray * S + lane * SPL + j] = w;
+    if (weights && valid) weights[ray * S + lane * SPL + j] = w;
     r = fmaf(w, c[j].x, r);
     g = fmaf(w, c[j].y, g);
     b = fmaf(w, c[j].z, b);
@@ -406,30 +410,49 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
     acc += __shfl_xor_sync(0xffffffffu, acc, o);
     dep += __shfl_xor_sync(0xffffffffu, dep, o);
   }
+  __shared__ __align__(16) float s_rows[8 * 5];
   if (lane == 0) {
     if (white_bkgd) {
       r += 1.f - acc;
       g += 1.f - acc;
       b += 1.f - acc;
     }
-    if (rgb_map) {
-      rgb_map[3 * ray] = r;
-      rgb_map[3 * ray + 1] = g;
-      rgb_map[3 * ray + 2] = b;
+    if (valid) {
+      if (rgb_map) {
+        rgb_map[3 * ray] = r;
+        rgb_map[3 * ray + 1] = g;
+        rgb_map[3 * ray + 2] = b;
+      }
+      if (acc_map) acc_map[ray] = acc;
+      if (depth_map) depth_map[ray] = dep;
+      if (disp_map) disp_map[ray] = 1.0f / fmaxf(1e-10f, dep / acc);
     }
-    if (acc_map) acc_map[ray] = acc;
-    if (depth_map) depth_map[ray] = dep;
-    if (disp_map) disp_map[ray] = 1.0f / fmaxf(1e-10f, dep / acc);
     if (peers.world > 0) {
-      const int64_t lc = ray / peers.chunk_rays;
-      const int64_t row = (lc * peers.world + peers.rank) * peers.chunk_rays + (ray - lc * peers.chunk_rays);
-      for (int k = 0; k < peers.world; ++k) {
-        float *dst = peers.maps[k] + row * 5;
-        dst[0] = r;
-        dst[1] = g;
-        dst[2] = b;
-        dst[3] = acc;
-        dst[4] = dep;
+      float *row = s_rows + (threadIdx.x >> 5) * 5;
+      row[0] = r;
+      row[1] = g;
+      row[2] = b;
+      row[3] = acc;
+      row[4] = dep;
+    }
+  }
+  if (peers.world > 0) {
+    // the block's 8 rays are 8 consecutive rows of one chunk: 160 contiguous, 16-byte aligned bytes per peer -> ten float4
+    // stores per peer (NVLink moves them as full packets; per-float remote stores cost ~5x the time)
+    __syncthreads();
+    const int64_t ray0 = (int64_t)blockIdx.x * 8;
+    const int nvalid = (int)min((int64_t)8, n_rays - ray0);
+    const int64_t lc = ray0 / peers.chunk_rays;
+    const int64_t row0 = (lc * peers.world + peers.rank) * peers.chunk_rays + (ray0 - lc * peers.chunk_rays);
+    if (nvalid == 8) {
+      if (threadIdx.x < 10 * peers.world) {
+        const int k = threadIdx.x / 10, q = threadIdx.x % 10;
+        reinterpret_cast<float4 *>(peers.maps[k] + row0 * 5)[q] = reinterpret_cast<const float4 *>(s_rows)[q];
+      }
+    } else {
+      for (int i = threadIdx.x; i < peers.world * nvalid * 5; i += blockDim.x) {
+        const int k = i / (nvalid * 5), j = i % (nvalid * 5);
+        peers.maps[k][row0 * 5 + j] = s_rows[j];
       }
     }
   }
