@@ -54,7 +54,8 @@ struct Step {          // one weight-ring stage worth of MMAs
   uint16_t a_chunk;    // first A chunk consumed
   uint16_t n_k16;      // K=16 MMAs (per pass) in this step
   uint16_t layer;
-  uint16_t flags;      // 1: first step of its layer, 2: last step of its layer
+  uint16_t flags;      // 1: first step of its (sub-)layer: fresh accumulator; 2: last step of its (sub-)layer: commit its acc barrier;
+                       // 4: (N-split, half B) the hidden quarters 0,1 of the A operand have been read for the last time: commit `bread`
 };
 
 struct LayerDev {
@@ -208,6 +209,7 @@ struct Cfg {
   static_assert(STAGES >= 2, "weight ring needs at least two stages");
   static constexpr int TMEM_COLS = 512;                         // NT = 2: one accumulator per slot; NT = 1: two, alternating by layer
   static constexpr int N_AREADY = NT == 1 ? 4 : NT;             // NT = 1: one per 64-column quarter of the hidden layer (quarter pipelining)
+  static constexpr int N_ACC = NT == 1 ? 3 : NT;                // NT = 1: acc of half A, acc of half B, `bread` (N-split)
   // offsets
   static constexpr int OFF_A_HI = 0;                            // slot t at t * A_BYTES
   static constexpr int OFF_A_LO = A_BYTES * NT;                 // only when NPASS == 3
@@ -236,11 +238,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + C::N_AREADY);
   // peer CTA only: its rows arrive here (cheap CTA-local arrives); one relay thread forwards each completed phase
   // to the leader's a_ready with a single cluster-scope arrive
-  const uint32_t bar_a_local = smem_u32(bars + 2 * C::STAGES + C::N_AREADY + NT);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2 * C::N_AREADY + NT);
-  static_assert((2 * C::STAGES + 2 * C::N_AREADY + NT + 1) * 8 <= 216, "barrier block overflow");
+  const uint32_t bar_a_local = smem_u32(bars + 2 * C::STAGES + C::N_AREADY + C::N_ACC);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 2 * C::N_AREADY + C::N_ACC);
+  static_assert((2 * C::STAGES + 2 * C::N_AREADY + C::N_ACC + 1) * 8 <= 216, "barrier block overflow");
   // QP (NT == 1): the epilogue of layer l publishes the next layer's A operand quarter by quarter (a_ready[q]) and the
   // accumulator alternates between two TMEM buffers, so the MMAs of layer l+1 start after the first quarter is written
+  // N-split (QP only): a 256-wide layer runs as two N=128 halves (A: output columns 0-127, then B), each with its own acc
+  // barrier.  The epilogue of half A (= quarters 0,1 of the next layer's K) overlaps the MMAs of half B, and the next layer's
+  // half A starts on quarters 0,1 while the epilogue of half B still produces quarters 2,3: the tensor pipe never waits for an
+  // epilogue.  The A operand is updated IN PLACE, so the epilogue of half A may only overwrite quarters 0,1 once half B's MMAs
+  // have read them: half B commits `bread` (bar_acc + 16) after its K steps over those quarters.
   constexpr bool QP = NT == 1;
   // last weight-stream position consumed from each ring stage: with one MMA thread per slot a thread only waits
   // on the `full` phases of its OWN steps, and a parity wait is only sound once the previous phase is known complete
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       mbar_init(bar_a_ready + 8 * t, ROW_THREADS + (PAIR == 2 ? 1 : 0));   // the leader's rows + the peer's relay
       mbar_init(bar_a_local + 8 * t, ROW_THREADS);
     }
-    for (int t = 0; t < NT; ++t) mbar_init(bar_acc + 8 * t, 1);
+    for (int t = 0; t < C::N_ACC; ++t) mbar_init(bar_acc + 8 * t, 1);
     for (int s = 0; s < C::STAGES; ++s) s_last[s] = 0xffffffffu;
     fence_barrier_init();
   }
@@ -332,12 +339,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && lane == 0;
         for (int l = 0; l < F.n_layers; ++l) {
           const int n_pad = F.layers[l].n_pad;
+          const int n_sub = (QP && n_pad == 256) ? 128 : n_pad;         // N of one MMA (N-split halves of a 256-wide layer)
           const int s0 = F.layers[l].step0, n_layer_steps = F.layers[l].n_steps;
-          const uint32_t idesc = instr_desc(n_pad, TILE_M * PAIR);
-          const uint32_t b_k_stride = (uint32_t)(n_pad / PAIR) * 16u;   // bytes between K core matrices (this CTA's rows)
+          const uint32_t idesc = instr_desc(n_sub, TILE_M * PAIR);
+          const uint32_t b_k_stride = (uint32_t)(n_sub / PAIR) * 16u;   // bytes between K core matrices (this CTA's rows)
           const uint32_t b_lbo = b_k_stride, b_sbo = 128u;
           g += (uint32_t)(t * n_layer_steps);                           // the earlier slots' copies of this layer
-          const uint32_t acc = tmem_base + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
+          uint32_t acc = tmem_base + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
+          int sub = 0;
           ANI_TRACE(8 + 16 * l + 8 * t + 4);
           // the A operand is ready (QP: its first quarter) and the accumulator has been drained
           int next_q = 1;
@@ -369,7 +378,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                 const uint32_t a_off = (uint32_t)(st.a_chunk + 2 * k) * CHUNK_BYTES;
                 const uint64_t adh = smem_desc(a_hi + a_off, a_lbo, a_sbo);
                 const uint64_t bdh = smem_desc(b_hi + (uint32_t)k * 2u * b_k_stride, b_lbo, b_sbo);
-                const uint32_t fresh = (s == s0 && k == 0) ? 0u : 1u;
+                const uint32_t fresh = ((st.flags & 1) && k == 0) ? 0u : 1u;
                 umma_bf16<PAIR>(acc, adh, bdh, idesc, fresh);
                 if (NPASS == 3) {
                   const uint64_t adl = smem_desc(a_lo + a_off, a_lbo, a_sbo);
@@ -380,7 +389,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               }
               if (NT > 1) s_last[stage] = g;
               umma_commit<PAIR>(bar_empty + 8 * stage);        // frees the ring stage (both CTAs) once these MMAs retire
-              if (s == s0 + n_layer_steps - 1) umma_commit<PAIR>(bar_acc + 8 * t);   // layer done for this slot: accumulators ready
+              if (st.flags & 4) umma_commit<PAIR>(bar_acc + 16);                  // half B is done with the A quarters 0,1
+              if (st.flags & 2) umma_commit<PAIR>(bar_acc + 8 * (QP ? sub : t));   // (half-)layer done: its accumulator columns are ready
+            }
+            if (st.flags & 2) {
+              ++sub;
+              acc += (uint32_t)n_sub;       // the next half's accumulator columns
             }
             __syncwarp();
           }
@@ -428,7 +442,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     // rows always arrive CTA-locally (per-warp aggregated arrives were measured slower: the __syncwarp lengthens every
     // quarter of the epilogue by more than the serialised arrives cost)
     const uint32_t a_arrive = leader ? bar_a_ready : bar_a_local;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, acc_b_phase = 0;
     for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
       const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
       if (args.trace && blockIdx.x == 0 && threadIdx.x == 0 && ut / n_units < 90) args.trace[160 + ut / n_units] = (unsigned long long)clock64();
@@ -515,7 +529,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           }
           if (!NERF && last) ANI_TRACE(5);
           ANI_TRACE(8 + 16 * l + 8 * t);
-          mbar_wait(bar_acc + 8 * t, acc_phase, 5 + 10 * t + 100 * l);
+          mbar_wait(bar_acc + 8 * (QP ? 0 : t), acc_phase, 5 + 10 * t + 100 * l);
           tc_fence_after();
           ANI_TRACE(8 + 16 * l + 8 * t + 1);
           if (!last) {
@@ -575,21 +589,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             };
             // this thread's i-th group of 32 columns: QP interleaves the row's two threads inside every quarter
             const int ga = QP ? half : half * 4, gs = QP ? 2 : 1;
-            tmem_ld32(t_acc + ga * 32, va);
-            tmem_ld_wait();
-            tmem_ld32(t_acc + (ga + gs) * 32, vb);
-            process(va, ga);
-            if (QP) publish(0);
-            tmem_ld_wait();
-            tmem_ld32(t_acc + (ga + 2 * gs) * 32, va);
-            process(vb, ga + gs);
-            if (QP) publish(1);
-            tmem_ld_wait();
-            tmem_ld32(t_acc + (ga + 3 * gs) * 32, vb);
-            process(va, ga + 2 * gs);
-            if (QP) publish(2);
-            tmem_ld_wait();
-            process(vb, ga + 3 * gs);
+            if (QP) {
+              // half A of the layer (output columns 0-127 = quarters 0,1 of the next K); half B's MMAs run meanwhile and still
+              // read the old quarters 0,1 until `bread`
+              tmem_ld32(t_acc + ga * 32, va);
+              tmem_ld_wait();
+              tmem_ld32(t_acc + (ga + gs) * 32, vb);
+              mbar_wait(bar_acc + 16, acc_b_phase, 9 + 100 * l);
+              process(va, ga);
+              publish(0);
+              tmem_ld_wait();
+              process(vb, ga + gs);
+              publish(1);
+              // half B (output columns 128-255 = quarters 2,3)
+              mbar_wait(bar_acc + 8, acc_b_phase, 10 + 100 * l);
+              tc_fence_after();
+              acc_b_phase ^= 1;
+              tmem_ld32(t_acc + (ga + 2 * gs) * 32, va);
+              tmem_ld_wait();
+              tmem_ld32(t_acc + (ga + 3 * gs) * 32, vb);
+              process(va, ga + 2 * gs);
+              publish(2);
+              tmem_ld_wait();
+              process(vb, ga + 3 * gs);
+            } else {
+              tmem_ld32(t_acc + ga * 32, va);
+              tmem_ld_wait();
+              tmem_ld32(t_acc + (ga + gs) * 32, vb);
+              process(va, ga);
+              tmem_ld_wait();
+              tmem_ld32(t_acc + (ga + 2 * gs) * 32, va);
+              process(vb, ga + gs);
+              tmem_ld_wait();
+              tmem_ld32(t_acc + (ga + 3 * gs) * 32, vb);
+              process(va, ga + 2 * gs);
+              tmem_ld_wait();
+              process(vb, ga + 3 * gs);
+            }
             if (alpha_layer && half == 1) xchg[row * 4] = sigma[t];   // read by the row's other thread after the next acc barrier
             publish(QP ? 3 : t);
             ANI_TRACE(8 + 16 * l + 8 * t + 2);
@@ -810,9 +846,14 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
   std::vector<uint8_t> image;
   for (size_t l = 0; l < H.size(); ++l) {
     const HostLayer &h = H[l];
-    const int n_half = h.n_pad / kPair;                     // weight rows held by each CTA of the pair
+    // the split-precision kernel (NT = 1) runs a 256-wide layer as two N=128 halves (see the kernel's N-split note)
+    const int n_subs = (npass == 3 && h.n_pad == 256) ? 2 : 1;
+    const int n_sub = h.n_pad / n_subs;
+    const int n_half = n_sub / kPair;                       // weight rows held by each CTA of the pair, per MMA
     const int per_step = std::max(1, hi_max / (n_half * 32));
     im.step0[l] = (int)steps.size();
+    for (int sub = 0; sub < n_subs; ++sub) {
+    bool bread_set = false;
     for (size_t si = 0; si < h.segs.size(); ++si) {
       const Segment &sg = h.segs[si];
       const int k16_total = sg.pad / 16;
@@ -827,6 +868,17 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
         s.n_k16 = (uint16_t)nk;
         s.layer = (uint16_t)l;
         s.flags = (uint16_t)(((si == 0 && k0 == 0) ? 1 : 0) | ((si + 1 == h.segs.size() && k0 + nk >= k16_total) ? 2 : 0));
+        if (n_subs == 2 && sub == 1 && !bread_set) {
+          // half B: after this step the hidden quarters 0,1 (A chunks HID_CHUNK0 .. HID_CHUNK0+15) are not read again
+          const bool reads_hidden = sg.a_chunk0 >= HID_CHUNK0;
+          const bool later_hidden = !reads_hidden && si + 1 < h.segs.size();      // a PE segment followed by the hidden segment
+          const bool covers = reads_hidden && (sg.a_chunk0 + 2 * (k0 + nk)) >= HID_CHUNK0 + 16;
+          const bool last_of_all = si + 1 == h.segs.size() && k0 + nk >= k16_total;
+          if ((covers || last_of_all) && !later_hidden) {
+            s.flags |= 4;
+            bread_set = true;
+          }
+        }
         image.resize(image.size() + s.bytes, 0);
         for (int r = 0; r < kPair; ++r) {           // image = [CTA0: hi, lo][CTA1: hi, lo]
           uint16_t *hi = reinterpret_cast<uint16_t *>(image.data() + s.w_off + r * cta_bytes);
@@ -834,7 +886,7 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
           for (int c = 0; c < nk * 2; ++c)          // 8-wide K chunk
             for (int nn = 0; nn < n_half; ++nn)
               for (int j = 0; j < 8; ++j) {
-                const int n = r * n_half + nn;
+                const int n = sub * n_sub + r * n_half + nn;
                 const int k = (k0 * 2 + c) * 8 + j;         // K index inside the segment
                 float w = 0.f;
                 if (n < h.n_out && k < sg.len) w = L[l].W[(size_t)n * h.k_in + sg.src0 + k];
@@ -846,6 +898,7 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
         }
         steps.push_back(s);
       }
+    }
     }
     im.n_layer_steps[l] = (int)steps.size() - im.step0[l];
   }
