@@ -186,6 +186,54 @@ __device__ __forceinline__ void write_pe(uint8_t *a_hi, uint8_t *a_lo, int chunk
   }
 }
 
+// Trilinear corner set for the SMPL-weight gather of the blend-weight head: same geometry as trilinear_corners()
+// (align_corners, border clamp) with the normalisation folded into one multiply by (dim-1)/ext -- the weights feed a
+// 1e-5-gated quantity, not a bit-exact mask, and the exact form's three IEEE divisions and rounding-order chain cost
+// ~3k cycles of dependent latency per row on the two-warps-per-scheduler epilogue threads.
+// gs: lo[3], scale[3] in shared memory.  off[k] is always a valid voxel (out-of-range corners have weight exactly 0).
+__device__ __forceinline__ void fast_corners(const float *gs, const int32_t dim[3], float px, float py, float pz, float w[8], int off[8]) {
+  const float p[3] = {px, py, pz};
+  float fl[3], fr[3];
+  int i0[3], i1[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lim = (float)(dim[a] - 1);
+    float u = (p[a] - gs[a]) * gs[3 + a];
+    u = fminf(lim, fmaxf(u, 0.0f));
+    const float f = floorf(u);
+    i0[a] = (int)f;
+    i1[a] = min(i0[a] + 1, dim[a] - 1);
+    fr[a] = u - f;
+    fl[a] = 1.0f - fr[a];
+  }
+  const int Y = dim[1], Z = dim[2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ex = k & 1, sy = (k >> 1) & 1, bz = (k >> 2) & 1;
+    w[k] = ((ex ? fr[2] : fl[2]) * (sy ? fr[1] : fl[1])) * (bz ? fr[0] : fl[0]);
+    off[k] = ((bz ? i1[0] : i0[0]) * Y + (sy ? i1[1] : i0[1])) * Z + (ex ? i1[2] : i0[2]);
+  }
+}
+
+// corner k (ATen order: k&1 east, k>>1&1 south, k>>2 bottom) of fast_corners(): its weight and voxel index
+__device__ __forceinline__ void fast_corner(const float *gs, const int32_t dim[3], float px, float py, float pz, int k, float &w, int &off) {
+  const float p[3] = {px, py, pz};
+  const int up[3] = {(k >> 2) & 1, (k >> 1) & 1, k & 1};   // axis 0 (X) <-> bottom, 1 (Y) <-> south, 2 (Z) <-> east
+  float wa[3];
+  int idx[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lim = (float)(dim[a] - 1);
+    const float u = fminf(lim, fmaxf((p[a] - gs[a]) * gs[3 + a], 0.0f));
+    const float f = floorf(u);
+    const float fr = u - f;
+    idx[a] = up[a] ? min((int)f + 1, dim[a] - 1) : (int)f;
+    wa[a] = up[a] ? fr : 1.0f - fr;
+  }
+  w = (wa[2] * wa[1]) * wa[0];
+  off = (idx[0] * dim[1] + idx[1]) * dim[2] + idx[2];
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -252,6 +300,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   // last weight-stream position consumed from each ring stage: with one MMA thread per slot a thread only waits
   // on the `full` phases of its OWN steps, and a parity wait is only sound once the previous phase is known complete
   volatile uint32_t *s_last = reinterpret_cast<volatile uint32_t *>(smem + C::OFF_BAR + 216);
+  float *s_grid = reinterpret_cast<float *>(smem + C::OFF_BAR + 232);   // lo[3], (dim-1)/ext [3] of the SMPL-weight volume
+  static_assert(C::STAGES * 4 <= 16, "s_last overlaps s_grid");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR == 2 ? cluster_ctarank() : 0u;
@@ -280,6 +330,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     for (int i = threadIdx.x; i < 644; i += N_THREADS) s_head[i] = F.head[i];
   } else if (args.A) {
     for (int i = threadIdx.x; i < 288; i += N_THREADS) s_head[i] = args.A[(i / 12) * 16 + (i % 12)];
+  }
+  if (!NERF && threadIdx.x < 3 && args.grid_bounds) {
+    const float lo = args.grid_bounds[threadIdx.x];
+    s_grid[threadIdx.x] = lo;
+    s_grid[3 + threadIdx.x] = (float)(args.grid_dim[threadIdx.x] - 1) / (args.grid_bounds[3 + threadIdx.x] - lo);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -449,6 +504,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       int64_t gi[NT];
       bool valid[NT];
       float px[NT], py[NT], pz[NT], sigma[NT];
+      float smpl[NT][ANINERF_N_BONES / 2];     // blend-weight head: the row's initial SMPL weights, 12 of the 24 bones per thread
       ANI_TRACE(0);
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
@@ -482,52 +538,48 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
           float *xchg = s_xchg + t * (TILE_M * 4);           // this slot's exchange between the row's two threads
           const uint32_t t_acc = t_lane + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
-          float smpl[ANINERF_N_BONES];
-          if (!NERF && last) ANI_TRACE(4);
-          if (!NERF && last && half == 0) {
-            // initial SMPL weights of this row, fetched while the last layer's MMAs run
+          if (!NERF && l < 8) {
+            // Initial SMPL weights of this row (this thread: bones 12*half .. +11): ONE trilinear corner per layer, fetched in
+            // the idle window before the layer's accumulator is ready and accumulated in registers (ATen's corner order).
+            // The whole gather is 98 KB per tile from L2, which also feeds the 1 MB weight stream: done in one burst it ran at
+            // the L2 bandwidth roof for 7-8k cycles and delayed the layer it shared the window with; 12 KB per window hides.
+            if (l == 0) {
+              ANI_TRACE(4);
 #pragma unroll
-            for (int k = 0; k < ANINERF_N_BONES; ++k) smpl[k] = 0.f;
+              for (int k = 0; k < ANINERF_N_BONES / 2; ++k) smpl[t][k] = 0.f;
+            }
             if (valid[t]) {
               if (args.smpl_bw) {
-                const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi[t] * ANINERF_N_BONES);
+                if (l == 7) {
+                  const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi[t] * ANINERF_N_BONES) + half * 3;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                  float4 w4 = __ldg(r4 + q);
-                  smpl[4 * q] = w4.x;
-                  smpl[4 * q + 1] = w4.y;
-                  smpl[4 * q + 2] = w4.z;
-                  smpl[4 * q + 3] = w4.w;
+                  for (int q = 0; q < 3; ++q) {
+                    float4 w4 = __ldg(r4 + q);
+                    smpl[t][4 * q] = w4.x;
+                    smpl[t][4 * q + 1] = w4.y;
+                    smpl[t][4 * q + 2] = w4.z;
+                    smpl[t][4 * q + 3] = w4.w;
+                  }
                 }
               } else {
-                float w[8];
-                int off[8];
-                VolumeGrid vg;
+                float wc;
+                int oc;
+                fast_corner(s_grid, args.grid_dim, px[t], py[t], pz[t], l, wc, oc);
+                const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)oc * ANINERF_N_BONES) + half * 3;
+                float4 c4[3];
 #pragma unroll
-                for (int a3 = 0; a3 < 3; ++a3) {
-                  vg.lo[a3] = __ldg(args.grid_bounds + a3);
-                  vg.ext[a3] = __fsub_rn(__ldg(args.grid_bounds + 3 + a3), vg.lo[a3]);
-                  vg.dim[a3] = args.grid_dim[a3];
-                }
-                trilinear_corners(vg, px[t], py[t], pz[t], w, off);
+                for (int q = 0; q < 3; ++q) c4[q] = __ldg(r4 + q);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  if (off[c] >= 0) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)off[c] * ANINERF_N_BONES);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                      float4 w4 = __ldg(r4 + q);
-                      smpl[4 * q] = __fadd_rn(smpl[4 * q], __fmul_rn(w4.x, w[c]));
-                      smpl[4 * q + 1] = __fadd_rn(smpl[4 * q + 1], __fmul_rn(w4.y, w[c]));
-                      smpl[4 * q + 2] = __fadd_rn(smpl[4 * q + 2], __fmul_rn(w4.z, w[c]));
-                      smpl[4 * q + 3] = __fadd_rn(smpl[4 * q + 3], __fmul_rn(w4.w, w[c]));
-                    }
-                  }
+                for (int q = 0; q < 3; ++q) {
+                  smpl[t][4 * q] = fmaf(c4[q].x, wc, smpl[t][4 * q]);
+                  smpl[t][4 * q + 1] = fmaf(c4[q].y, wc, smpl[t][4 * q + 1]);
+                  smpl[t][4 * q + 2] = fmaf(c4[q].z, wc, smpl[t][4 * q + 2]);
+                  smpl[t][4 * q + 3] = fmaf(c4[q].w, wc, smpl[t][4 * q + 3]);
                 }
               }
             }
+            if (l == 7) ANI_TRACE(5);
           }
-          if (!NERF && last) ANI_TRACE(5);
           ANI_TRACE(8 + 16 * l + 8 * t);
           mbar_wait(bar_acc + 8 * (QP ? 0 : t), acc_phase, 5 + 10 * t + 100 * l);
           tc_fence_after();
@@ -631,53 +683,70 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             ANI_TRACE(8 + 16 * l + 8 * t + 2);
           } else if (!NERF) {
             // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
-            if (half == 0) {
-              uint32_t v[32];
-              tmem_ld32(t_acc, v);
-              tmem_ld_wait();
-              tc_fence_before();
-              float bw[ANINERF_N_BONES];
-              float mx = -INFINITY;
+            // The row's two threads take 12 bones each and meet three times (max, sum, skinning matrix) through a scratch
+            // area in the A operand, which is dead until the next tile's input encoding.
+            uint32_t v[32];
+            tmem_ld32(t_acc, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            float *scr = reinterpret_cast<float *>(a_hi + 8 * CHUNK_BYTES);   // exchange scratch: the hidden chunks (all MMAs have retired)
+            constexpr int HB = ANINERF_N_BONES / 2;
+            const int k0 = half * HB;
+            float bw[HB];
+            float mx = -INFINITY;
 #pragma unroll
-              for (int k = 0; k < ANINERF_N_BONES; ++k) {
-                bw[k] = logf(smpl[k] + 1e-9f) + (__uint_as_float(v[k]) + bias[k]);
-                mx = fmaxf(mx, bw[k]);
+            for (int k = 0; k < HB; ++k) {
+              const float d = __uint_as_float(half ? v[HB + k] : v[k]);
+              bw[k] = logf(smpl[t][k] + 1e-9f) + (d + bias[k0 + k]);
+              mx = fmaxf(mx, bw[k]);
+            }
+            scr[half * TILE_M + row] = mx;
+            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+            mx = fmaxf(scr[row], scr[TILE_M + row]);
+            float part = 0.f;
+#pragma unroll
+            for (int k = 0; k < HB; ++k) {
+              bw[k] = expf(bw[k] - mx);
+              part += bw[k];
+            }
+            scr[(2 + half) * TILE_M + row] = part;
+            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+            const float inv_sum = 1.0f / (scr[2 * TILE_M + row] + scr[3 * TILE_M + row]);
+#pragma unroll
+            for (int k = 0; k < HB; ++k) bw[k] *= inv_sum;
+            if (valid[t] && args.bw_out) {
+              float4 *o4 = reinterpret_cast<float4 *>(args.bw_out + gi[t] * ANINERF_N_BONES) + half * 3;
+#pragma unroll
+              for (int q = 0; q < 3; ++q) o4[q] = make_float4(bw[4 * q], bw[4 * q + 1], bw[4 * q + 2], bw[4 * q + 3]);
+            }
+            if (args.tpts_out) {
+              float M[12];
+#pragma unroll
+              for (int j = 0; j < 12; ++j) M[j] = 0.f;
+#pragma unroll
+              for (int k = 0; k < HB; ++k)
+#pragma unroll
+                for (int j = 0; j < 12; ++j) M[j] = fmaf(bw[k], s_head[(k0 + k) * 12 + j], M[j]);
+              if (half == 1) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) scr[(4 + j) * TILE_M + row] = M[j];
               }
-              float sum = 0.f;
+              asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+              if (half == 0 && valid[t]) {
 #pragma unroll
-              for (int k = 0; k < ANINERF_N_BONES; ++k) {
-                bw[k] = expf(bw[k] - mx);
-                sum += bw[k];
-              }
-              const float inv_sum = 1.0f / sum;
-#pragma unroll
-              for (int k = 0; k < ANINERF_N_BONES; ++k) bw[k] *= inv_sum;
-              if (valid[t]) {
-                if (args.bw_out) {
-                  float4 *o4 = reinterpret_cast<float4 *>(args.bw_out + gi[t] * ANINERF_N_BONES);
-#pragma unroll
-                  for (int q = 0; q < 6; ++q) o4[q] = make_float4(bw[4 * q], bw[4 * q + 1], bw[4 * q + 2], bw[4 * q + 3]);
-                }
-                if (args.tpts_out) {
-                  float M[12];
-#pragma unroll
-                  for (int j = 0; j < 12; ++j) M[j] = 0.f;
-#pragma unroll
-                  for (int k = 0; k < ANINERF_N_BONES; ++k)
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) M[j] = fmaf(bw[k], s_head[k * 12 + j], M[j]);
-                  float qx = px[t] - M[3], qy = py[t] - M[7], qz = pz[t] - M[11];
-                  float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], kk = M[10];
-                  float c00 = e * kk - f * h, c01 = c * h - b * kk, c02 = b * f - c * e;
-                  float c10 = f * g - d * kk, c11 = a * kk - c * g, c12 = c * d - a * f;
-                  float c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
-                  float inv = 1.0f / (a * c00 + b * c10 + c * c20);
-                  args.tpts_out[3 * gi[t]] = (c00 * qx + c01 * qy + c02 * qz) * inv;
-                  args.tpts_out[3 * gi[t] + 1] = (c10 * qx + c11 * qy + c12 * qz) * inv;
-                  args.tpts_out[3 * gi[t] + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
-                }
+                for (int j = 0; j < 12; ++j) M[j] += scr[(4 + j) * TILE_M + row];
+                float qx = px[t] - M[3], qy = py[t] - M[7], qz = pz[t] - M[11];
+                float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], kk = M[10];
+                float c00 = e * kk - f * h, c01 = c * h - b * kk, c02 = b * f - c * e;
+                float c10 = f * g - d * kk, c11 = a * kk - c * g, c12 = c * d - a * f;
+                float c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+                float inv = 1.0f / (a * c00 + b * c10 + c * c20);
+                args.tpts_out[3 * gi[t]] = (c00 * qx + c01 * qy + c02 * qz) * inv;
+                args.tpts_out[3 * gi[t] + 1] = (c10 * qx + c11 * qy + c12 * qz) * inv;
+                args.tpts_out[3 * gi[t] + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
               }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // the scratch is the next tile's PE operand
           } else {
             // ---- NeRF head: view layer (ReLU) -> rgb_fc in fp32; alpha from the layer-7 epilogue ---
             float rgb[3] = {0.f, 0.f, 0.f};
