@@ -116,6 +116,7 @@ PROTOTYPES = {
     'aninerf_sample_blend_weights_backward': (_I32, [_VP, _I64, _VP, C.POINTER(_I32), _VP, _VP, _VP, _I32, _VP]),
     'aninerf_nerf_tail_forward': (_I32, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     'aninerf_nerf_tail_backward': (_I32, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    'aninerf_mask_sigma': (_I32, [_VP, _VP, _VP, _VP, _I64, _F, _I64, _VP, _VP]),
     'aninerf_composite_backward': (_I32, [_VP, _VP, _I64, _I32, _I32, _VP, _VP]),
     'aninerf_img_loss': (_I32, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     'aninerf_select_rows': (_I32, [_VP, _VP, _I32, _F, _VP, _VP, _VP]),

@@ -214,6 +214,19 @@ __global__ void __launch_bounds__(256) nerf_tail_backward_kernel(const float4 *_
   d_sigma[i] = (inside && sg > 0.f) ? g.w * dists[i] * expf(-sg * dists[i]) : 0.f;
 }
 
+// stage-2 trainer (aninerf_animation_trainer.py:73-82): alpha[outside] = 0 with outside = !(tpose strictly inside tbounds
+// && pnorm < norm_th); pnorm = channel 24 of the sampled posed-volume rows (leading dimension ld), or null
+__global__ void __launch_bounds__(256) mask_sigma_kernel(const float *__restrict__ sigma, const float *__restrict__ tpts, const float *__restrict__ tbounds,
+                                                         const float *__restrict__ pnorm, int64_t ld, float norm_th, int64_t n,
+                                                         float *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = tpts[3 * i], y = tpts[3 * i + 1], z = tpts[3 * i + 2];
+  bool inside = x > tbounds[0] && x < tbounds[3] && y > tbounds[1] && y < tbounds[4] && z > tbounds[2] && z < tbounds[5];
+  if (pnorm) inside = inside && pnorm[i * ld] < norm_th;
+  out[i] = inside ? sigma[i] : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // raw2outputs backward (nerf_net_utils.py:6-36), gradient of rgb_map only (the loss uses nothing else):
 //   w_i = a_i T_i, T_i = prod_{j<i} (1 - a_j + 1e-10);  e_i = g.c_i (- sum g with a white background)
@@ -466,6 +479,15 @@ int aninerf_nerf_tail_backward(const float *d_raw_full, const float *raw_full, c
   if (n == 0) return ANINERF_OK;
   nerf_tail_backward_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>((const float4 *)d_raw_full, (const float4 *)raw_full, index, sigma_masked,
                                                                             tpts, tbounds, dists, n, d_sigma, d_rgb);
+  ANI_LAUNCHED();
+  return ANINERF_OK;
+}
+
+int aninerf_mask_sigma(const float *sigma, const float *tpts, const float *tbounds, const float *pnorm, int64_t ld, float norm_th, int64_t n,
+                       float *out, void *stream) {
+  ANI_CHECK_ARG(sigma && tpts && tbounds && out && n >= 0);
+  if (n == 0) return ANINERF_OK;
+  mask_sigma_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(sigma, tpts, tbounds, pnorm, ld, norm_th, n, out);
   ANI_LAUNCHED();
   return ANINERF_OK;
 }

@@ -83,16 +83,19 @@ class _Trunk:
         self.pe, self.H, self.latv = pe, H, lat
         return H[8]
 
-    def backward(self, dZ, g_lat, d_pe):
+    def backward(self, dZ, g_lat, d_pe, wgrad=True):
         """dZ (n,256): gradient of layer 7's pre-activation.  g_lat (1,128) gradient row of the latent code (accumulated) or None.
-        d_pe (n,>=63) or None: receives the gradient of the PE input (written, not accumulated)."""
+        d_pe (n,>=63) or None: receives the gradient of the PE input (written, not accumulated).
+        wgrad=False: a frozen field (stage-2 training) -- only the data gradients are propagated."""
         n, dev = dZ.shape[0], dZ.device
         H, pe = self.H, self.pe
         sk = T.split_for(n)
         for l in range(7, -1, -1):
             W, gW = self.W[l], self.gW[l]
             # weight gradients  dW[seg] += dZ^T @ X_seg
-            if l == 0:
+            if not wgrad:
+                pass
+            elif l == 0:
                 T.gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, split_k=sk)
             elif l == 5:
                 T.gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, split_k=sk)
@@ -100,7 +103,9 @@ class _Trunk:
             else:
                 T.gemm([(Op(dZ).T, Op(H[l]).T)], gW, accumulate=True, split_k=sk)
             # bias (and folded latent) gradients
-            if self.lat and l in (0, 5):
+            if not wgrad:
+                pass
+            elif self.lat and l in (0, 5):
                 db = T.colsum(dZ, torch.empty(1, 256, device=dev))
                 self.gb[l].add_(db.view(-1))
                 Wl = W[:, 63:63 + self.lat]

@@ -131,3 +131,29 @@ def sample_volume_backward(pts, vol, bounds, d_out24, d_pts, accumulate):
     dims = (C.c_int32 * 3)(*vol.shape[-4:-1])
     _lib.check(_lib.lib().aninerf_sample_blend_weights_backward(_lib.ptr(pts), pts.shape[0], _lib.ptr(vol), dims, _lib.ptr(bounds), _lib.ptr(d_out24),
                                                                 _lib.ptr(d_pts), int(accumulate), _lib.stream_ptr(pts.device)))
+
+
+def world_to_pose(wpts, R, Th, out):
+    _lib.check(_lib.lib().aninerf_world_to_pose(_lib.ptr(wpts), wpts.shape[0], _lib.ptr(R), _lib.ptr(Th), _lib.ptr(out), _lib.stream_ptr(wpts.device)))
+    return out
+
+
+def forward_lbs(tpts, bw, A, ppts):
+    _lib.check(_lib.lib().aninerf_forward_lbs(_lib.ptr(tpts), _lib.ptr(bw), tpts.shape[0], _lib.ptr(A), _lib.ptr(ppts), _lib.stream_ptr(tpts.device)))
+    return ppts
+
+
+def mask_sigma(sigma, tpts, tbounds, pnorm, ld, norm_th, out):
+    _lib.check(_lib.lib().aninerf_mask_sigma(_lib.ptr(sigma), _lib.ptr(tpts), _lib.ptr(tbounds), _lib.ptr(pnorm), ld, float(norm_th), tpts.shape[0],
+                                             _lib.ptr(out), _lib.stream_ptr(tpts.device)))
+    return out
+
+
+def select_rows(sigma_masked, chunk_offsets, n_chunks, train_th, sel, n_sel):
+    _lib.check(_lib.lib().aninerf_select_rows(_lib.ptr(sigma_masked), _lib.ptr(chunk_offsets), n_chunks, float(train_th), _lib.ptr(sel), _lib.ptr(n_sel),
+                                              _lib.stream_ptr(sel.device)))
+
+
+def bw_loss(pbw, tbw, sel, n_sel, loss, d_pbw, d_tbw):
+    _lib.check(_lib.lib().aninerf_bw_loss(_lib.ptr(pbw), _lib.ptr(tbw), _lib.ptr(sel), _lib.ptr(n_sel), pbw.shape[0], _lib.ptr(loss), _lib.ptr(d_pbw),
+                                          _lib.ptr(d_tbw), _lib.stream_ptr(pbw.device)))

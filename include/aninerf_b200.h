@@ -351,6 +351,10 @@ int aninerf_nerf_tail_forward(const float *sigma, const float *rgb, const float 
 int aninerf_nerf_tail_backward(const float *d_raw_full, const float *raw_full, const int32_t *index, const float *sigma_masked,
                                const float *tpts, const float *tbounds, const float *dists, int64_t n, float *d_sigma, float *d_rgb,
                                void *stream);
+/* Stage-2 trainer (lib/train/trainers/aninerf_animation_trainer.py:73-82): out = sigma where the canonical point lies strictly
+ * inside tbounds and (pnorm given) pnorm[i*ld] < norm_th, else 0. */
+int aninerf_mask_sigma(const float *sigma, const float *tpts, const float *tbounds, const float *pnorm, int64_t ld, float norm_th,
+                       int64_t n, float *out, void *stream);
 /* Backward of raw2outputs (nerf_net_utils.py:6-36) for a gradient arriving on rgb_map. d_raw (n_rays,S,4). */
 int aninerf_composite_backward(const float *raw, const float *d_rgb_map, int64_t n_rays, int32_t n_samples, int32_t white_bkgd,
                                float *d_raw, void *stream);

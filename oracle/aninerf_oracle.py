@@ -412,6 +412,60 @@ def train_step_grads(sd, batch, cfg=None, t_rand=None, clip=40.0):
 
 
 # ----------------------------------------------------------------------------
+# stage 2: novel-pose blend-weight training  -- lib/train/trainers/aninerf_animation_trainer.py:11-152
+# ----------------------------------------------------------------------------
+def _select_rows(alpha, train_th):
+    ind = alpha.detach() > train_th
+    ind[torch.arange(alpha.size(0)), torch.argmax(alpha, dim=1)] = True
+    return ind
+
+
+def animation_train_loss(sd, batch, wpts, tpts, cfg=None):
+    """NetworkWrapper.forward of the second training stage.  wpts / tpts (1,n,3): the uniform samples of wbounds / tbounds
+    that get_sampling_points draws with torch.rand (:122-142), passed in for parity.  Only `novel_pose_bw.*` is trained."""
+    cfg = cfg or OracleCfg()
+    idx = batch['bw_latent_index']
+    zero = torch.zeros_like(idx)
+    # observation space -> canonical (ppts_to_tpose, :56-91)
+    ppts = world_to_pose(wpts, batch['R'], batch['Th'])
+    pv = sample_blend_weights(ppts, batch['pbw'], batch['pbounds'])
+    init_pbw, pnorm = pv[:, :24], pv[:, 24]
+    pbw = neural_blend_weights(sd, ppts, init_pbw, idx, prefix='novel_pose_bw.', xyz_res=cfg.xyz_res)
+    tpose = inverse_lbs(ppts, pbw, batch['A'])
+    init_tbw = sample_blend_weights(tpose, batch['tbw'], batch['tbounds'])[:, :24]
+    tbw = neural_blend_weights(sd, tpose, init_tbw, zero, xyz_res=cfg.xyz_res)
+    alpha = nerf_alpha(sd, tpose, xyz_res=cfg.xyz_res)
+    inside = torch.sum((tpose > batch['tbounds'][:, :1]) * (tpose < batch['tbounds'][:, 1:]), dim=2) == 3
+    inside = inside * (pnorm < cfg.norm_th)
+    alpha = alpha[:, 0].clone()
+    alpha[~inside] = 0
+    sel0 = _select_rows(alpha, cfg.train_th)
+    pbw0, tbw0 = pbw.transpose(1, 2)[sel0], tbw.transpose(1, 2)[sel0]
+    # canonical space -> observation (tpose_to_ppts, :94-119)
+    init_tbw1 = sample_blend_weights(tpts, batch['tbw'], batch['tbounds'])[:, :24]
+    tbw_c = neural_blend_weights(sd, tpts, init_tbw1, zero, xyz_res=cfg.xyz_res)
+    alpha1 = nerf_alpha(sd, tpts, xyz_res=cfg.xyz_res)[:, 0]
+    pose_pts = forward_lbs(tpts, tbw_c, batch['A'])
+    init_pbw1 = sample_blend_weights(pose_pts, batch['pbw'], batch['pbounds'])[:, :24]
+    pbw_c = neural_blend_weights(sd, pose_pts, init_pbw1, idx, prefix='novel_pose_bw.', xyz_res=cfg.xyz_res)
+    sel1 = _select_rows(alpha1, cfg.train_th)
+    pbw1, tbw1 = pbw_c.transpose(1, 2)[sel1], tbw_c.transpose(1, 2)[sel1]
+    l0 = F.smooth_l1_loss(pbw0, tbw0)
+    l1 = F.smooth_l1_loss(pbw1, tbw1)
+    loss = l0 + l1
+    return {'pbw0': pbw0}, loss, {'bw_loss0': l0, 'bw_loss1': l1, 'loss': loss}
+
+
+def animation_train_step_grads(sd, batch, wpts, tpts, cfg=None, clip=40.0):
+    """One stage-2 iteration up to the optimizer: only novel_pose_bw.* requires grad (:26-31)."""
+    params = {k: (v.detach().clone().requires_grad_(k.startswith('novel_pose_bw.'))) for k, v in sd.items()}
+    _, loss, stats = animation_train_loss(params, batch, wpts, tpts, cfg)
+    loss.backward()
+    grads = {k: v.grad.clamp(-clip, clip) for k, v in params.items() if k.startswith('novel_pose_bw.') and v.grad is not None}
+    return {k: float(v) for k, v in stats.items()}, grads
+
+
+# ----------------------------------------------------------------------------
 # novel-view / pose-sequence renderer with multi-view silhouette culling
 # -- lib/networks/renderer/tpose_renderer_mmsk.py:14-166
 # ----------------------------------------------------------------------------

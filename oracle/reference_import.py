@@ -80,6 +80,11 @@ def load(cfg_file='configs/aninerf_313.yaml', overrides=()):
             from lib.utils import render_utils
         except Exception as e:  # noqa: BLE001
             print('reference_import: render_utils not importable:', e)
+        anim_trainer_mod = None
+        try:
+            from lib.train.trainers import aninerf_animation_trainer as anim_trainer_mod
+        except Exception as e:  # noqa: BLE001
+            print('reference_import: aninerf_animation_trainer not importable:', e)
         trainer_mod = None
         try:
             from lib.train.trainers import tpose_trainer as trainer_mod
@@ -94,5 +99,5 @@ def load(cfg_file='configs/aninerf_313.yaml', overrides=()):
             os.environ['CUDA_VISIBLE_DEVICES'] = saved_cvd
     _loaded = types.SimpleNamespace(cfg=cfg, Network=net_mod.Network, Renderer=ren_mod.Renderer,
                                     net_mod=net_mod, dutils=dutils, nerf_net_utils=nerf_net_utils,
-                                    blend_utils=blend_utils, embedder=embedder, MmskRenderer=mmsk_mod.Renderer, trainer_mod=trainer_mod, render_utils=render_utils)
+                                    blend_utils=blend_utils, embedder=embedder, MmskRenderer=mmsk_mod.Renderer, trainer_mod=trainer_mod, render_utils=render_utils, anim_trainer_mod=anim_trainer_mod)
     return _loaded

@@ -251,6 +251,41 @@ def main():
            all(biteq(out_r2[k].numpy(), out_o2[k].numpy()) for k in keys), 'all 6 outputs bit-equal')
     np.savez_compressed(os.path.join(GOLDEN, 'render_small_novel_pose.npz'), sd_seed=1, sd_digest=sd_digest(sd2), num_eval_frame=8,
                         **{k: out_r2[k].numpy() for k in ('rgb_map', 'acc_map', 'depth_map')})
+    # ---------------- stage 2: novel-pose blend-weight training (aninerf_animation_trainer) -----------------
+    if ref.anim_trainer_mod is not None:
+        import unittest.mock as mock
+        n_pts = 4096
+        gen = torch.Generator().manual_seed(6)
+        draws = [torch.rand(1, n_pts, generator=gen) for _ in range(6)]
+        wb, tbd = batch['wbounds'], batch['tbounds']
+        wpts = (wb[:, 1] - wb[:, 0])[:, None] * torch.stack(draws[0:3], dim=2) + wb[:, 0][:, None]
+        tpts_s = (tbd[:, 1] - tbd[:, 0])[:, None] * torch.stack(draws[3:6], dim=2) + tbd[:, 0][:, None]
+        it = iter(draws)
+        cwd = os.getcwd()
+        os.chdir(reference_import.REF)
+        try:
+            wrapper2 = ref.anim_trainer_mod.NetworkWrapper(net2)
+        finally:
+            os.chdir(cwd)
+        net2.zero_grad()
+        # the reference draws 1024*64 points with torch.rand; feed it our (smaller) seeded draws instead
+        with mock.patch.object(ref.anim_trainer_mod.torch, 'rand', side_effect=lambda *a, **k: next(it)):
+            _, loss2, stats2, _ = wrapper2(batch)
+        loss2.mean().backward()
+        torch.nn.utils.clip_grad_value_(net2.parameters(), 40)
+        g_r = {k: p.grad.clone() for k, p in net2.named_parameters() if p.grad is not None}
+        st_o, g_o = O.animation_train_step_grads(sd2, batch, wpts, tpts_s, O.OracleCfg())
+        ok = set(g_r) == set(g_o) and all(biteq(g_r[k].numpy(), g_o[k].numpy()) for k in g_r) and \
+            all(float(stats2[k]) == st_o[k] for k in ('bw_loss0', 'bw_loss1', 'loss'))
+        report('aninerf_animation_trainer step: 2 losses + novel_pose_bw gradients', 'aninerf_animation_trainer.py:33-119', ok,
+               f'bit-equal ({len(g_r)} trainable tensors; loss {st_o["loss"]:.6e} = {st_o["bw_loss0"]:.3e} + {st_o["bw_loss1"]:.3e})')
+        np.savez_compressed(os.path.join(GOLDEN, 'animation_train_step_small.npz'), wpts=wpts[0].numpy(), tpts=tpts_s[0].numpy(),
+                            **{'stat_' + k: np.float32(float(stats2[k])) for k in ('bw_loss0', 'bw_loss1', 'loss')},
+                            **{'grad_' + k: g_r[k].numpy() for k in ('novel_pose_bw.bw_fc.weight', 'novel_pose_bw.bw_fc.bias',
+                                                                     'novel_pose_bw.bw_linears.0.bias', 'novel_pose_bw.bw_latent.weight')},
+                            **{'gradnorm_' + k: np.float32(float(g_r[k].norm())) for k in g_r})
+        for prm in net2.parameters():
+            prm.requires_grad = True
     cfg.test_novel_pose = False
     cfg.aninerf_animation = False
 

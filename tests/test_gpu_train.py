@@ -91,3 +91,38 @@ def test_train_iteration_reduces_the_loss(dev):
     w.net.eval()
     out = w.renderer.render(b)
     assert torch.isfinite(out['rgb_map']).all()
+
+
+def test_animation_train_step_matches_reference_and_oracle(dev):
+    """Stage 2 (aninerf_animation_trainer): two blend-weight consistency losses, gradients of novel_pose_bw.* only."""
+    from animatable_nerf_b200 import config, synthetic
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.aninerf_animation_trainer import NetworkWrapper
+    _, batch, _ = golden_small_case()
+    g2 = load_golden('render_small_novel_pose.npz')
+    ga = load_golden('animation_train_step_small.npz')
+    sd2 = synthetic.make_state_dict(seed=int(g2['sd_seed']), num_eval_frame=int(g2['num_eval_frame']))
+    cfg = config.make_cfg(perturb=0., aninerf_animation=True, num_eval_frame=int(g2['num_eval_frame']))
+    net = Network(cfg)
+    net.load_state_dict(sd2)
+    net = net.to(dev).train()
+    w = NetworkWrapper(net, cfg)
+    wpts, tpts = torch.from_numpy(ga['wpts']), torch.from_numpy(ga['tpts'])
+    ret, loss, stats, _ = w(to_device(batch, dev), wpts=wpts, tpts=tpts)
+    loss.mean().backward()
+    torch.nn.utils.clip_grad_value_(net.parameters(), 40)
+    for k in ('bw_loss0', 'bw_loss1', 'loss'):
+        assert abs(float(stats[k]) - float(ga['stat_' + k])) <= 1e-6, (k, float(stats[k]), float(ga['stat_' + k]))
+    grads = {k: p.grad.detach().cpu() for k, p in net.named_parameters() if p.grad is not None}
+    assert all(k.startswith('novel_pose_bw.') for k in grads) and len(grads) == 19
+    for k in [f[5:] for f in ga.files if f.startswith('grad_')]:
+        ref = torch.from_numpy(ga['grad_' + k])
+        err = float((grads[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+        assert err <= GRAD_TOL, (k, err)
+    stats_o, grads_o = O.animation_train_step_grads(sd2, batch, wpts[None], tpts[None], O.OracleCfg())
+    worst = ('', 0.0)
+    for k, ref in grads_o.items():
+        err = float((grads[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+        worst = max(worst, (k, err), key=lambda kv: kv[1])
+        assert err <= GRAD_TOL, (k, err)
+    print('stage-2 worst gradient error', worst, 'loss', float(loss), stats_o['loss'])
