@@ -350,7 +350,11 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
                                                         const float *__restrict__ t_vals, int64_t n_rays, int white_bkgd,
                                                         float *__restrict__ rgb_map, float *__restrict__ acc_map,
                                                         float *__restrict__ depth_map, float *__restrict__ disp_map,
-                                                        float *__restrict__ weights, PeerScatter peers) {
+                                                        float *__restrict__ weights, PeerScatter peers,
+                                                        const uint32_t *__restrict__ mask_words, const int32_t *__restrict__ block_offsets) {
+  // mask_words != nullptr: `raw` holds only the ACTIVE samples, compacted in ascending sample order (the render-only path never
+  // materialises the dense (n,4) buffer); a ray's rows start at block_offsets[its 2048-sample block] + the active samples of
+  // the block before it, and an inactive sample contributes exactly what a zero row of the dense buffer would.
   constexpr int S = 32 * SPL;
   int lane = threadIdx.x & 31;
   int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -359,10 +363,48 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
     if (peers.world == 0) return;
     ray = n_rays - 1;            // the peer scatter below needs the whole block at its __syncthreads: compute a dummy, write nothing
   }
+  float r = 0.f, g = 0.f, b = 0.f, acc = 0.f, dep = 0.f;
+  bool empty = false;            // compact mode: a ray without a single active sample composites to exact zeros (w = 0 * T)
+  if (mask_words) {
+    uint32_t any = 0u;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) any |= __ldg(mask_words + ray * SPL + j);
+    empty = any == 0u;
+  }
+  if (!empty) {
   float4 c[SPL];
   float z[SPL];
+  if (mask_words) {
+    constexpr int WPB = 2048 / 32;                          // mask words per 2048-sample block (MB below)
+    const int64_t w0 = ray * SPL;                           // first mask word of the ray (S/32 = SPL words per ray)
+    const int64_t blk = (ray * S) / 2048;
+    const int64_t bw0 = blk * WPB;
+    int before = 0;
+    for (int64_t i = bw0 + lane; i < w0; i += 32) before += __popc(__ldg(mask_words + i));
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) c[j] = __ldg(raw + ray * S + lane * SPL + j);
+    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    int64_t pos = (int64_t)__ldg(block_offsets + blk) + before;
+    uint32_t mw[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) mw[j] = __ldg(mask_words + w0 + j);
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const int sidx = lane * SPL + j;                      // sample index within the ray
+      const int word = sidx >> 5, bit = sidx & 31;
+      int64_t p = pos;
+      uint32_t m = 0u;
+#pragma unroll
+      for (int q = 0; q < SPL; ++q) {      // constant indices only (no local-memory copy of mw)
+        if (q < word) p += __popc(mw[q]);
+        if (q == word) m = mw[q];
+      }
+      p += __popc(m & ((1u << bit) - 1u));
+      c[j] = ((m >> bit) & 1u) ? __ldg(raw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) c[j] = __ldg(raw + ray * S + lane * SPL + j);
+  }
   if (z_vals) {
 #pragma unroll
     for (int j = 0; j < SPL; ++j) z[j] = __ldg(z_vals + ray * S + lane * SPL + j);
@@ -390,7 +432,6 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
   }
   float T = __shfl_up_sync(0xffffffffu, inc, 1);
   if (lane == 0) T = 1.f;
-  float r = 0.f, g = 0.f, b = 0.f, acc = 0.f, dep = 0.f;
 #pragma unroll
   for (int j = 0; j < SPL; ++j) {
     float w = c[j].w * T;
@@ -410,6 +451,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
     acc += __shfl_xor_sync(0xffffffffu, acc, o);
     dep += __shfl_xor_sync(0xffffffffu, dep, o);
   }
+  }   // !empty
   __shared__ __align__(16) float s_rows[8 * 5];
   if (lane == 0) {
     if (white_bkgd) {
@@ -444,15 +486,24 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4 *__restrict
     const int nvalid = (int)min((int64_t)8, n_rays - ray0);
     const int64_t lc = ray0 / peers.chunk_rays;
     const int64_t row0 = (lc * peers.world + peers.rank) * peers.chunk_rays + (ray0 - lc * peers.chunk_rays);
+    // (constant indices only: a dynamically indexed kernel-parameter array is copied to local memory by every thread)
     if (nvalid == 8) {
       if (threadIdx.x < 10 * peers.world) {
-        const int k = threadIdx.x / 10, q = threadIdx.x % 10;
-        reinterpret_cast<float4 *>(peers.maps[k] + row0 * 5)[q] = reinterpret_cast<const float4 *>(s_rows)[q];
+        const int kk = threadIdx.x / 10, q = threadIdx.x % 10;
+        float *base = nullptr;
+#pragma unroll
+        for (int k = 0; k < ANINERF_MAX_PEERS; ++k)
+          if (k == kk) base = peers.maps[k];
+        reinterpret_cast<float4 *>(base + row0 * 5)[q] = reinterpret_cast<const float4 *>(s_rows)[q];
       }
     } else {
       for (int i = threadIdx.x; i < peers.world * nvalid * 5; i += blockDim.x) {
-        const int k = i / (nvalid * 5), j = i % (nvalid * 5);
-        peers.maps[k][row0 * 5 + j] = s_rows[j];
+        const int kk = i / (nvalid * 5), j = i % (nvalid * 5);
+        float *base = nullptr;
+#pragma unroll
+        for (int k = 0; k < ANINERF_MAX_PEERS; ++k)
+          if (k == kk) base = peers.maps[k];
+        base[row0 * 5 + j] = s_rows[j];
       }
     }
   }
@@ -961,10 +1012,10 @@ int aninerf_composite(const float *raw, const float *z_vals, int64_t n_rays, int
   cudaStream_t st = (cudaStream_t)stream;
   if (S == 64)
     composite_kernel<2><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, nullptr, nullptr, nullptr, n_rays, white_bkgd, rgb_map,
-                                                acc_map, depth_map, disp_map, weights, PeerScatter{});
+                                                acc_map, depth_map, disp_map, weights, PeerScatter{}, nullptr, nullptr);
   else
     composite_kernel<1><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, nullptr, nullptr, nullptr, n_rays, white_bkgd, rgb_map,
-                                                acc_map, depth_map, disp_map, weights, PeerScatter{});
+                                                acc_map, depth_map, disp_map, weights, PeerScatter{}, nullptr, nullptr);
   ANI_LAUNCHED();
   return ANINERF_OK;
 }
@@ -1028,7 +1079,7 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
 
 int launch_composite_fused(const float *raw, const float *near, const float *far, const float *t_vals, const float *z_vals, int64_t n_rays,
                            int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, const aninerf_peer_gather *peers,
-                           int chunk_rays, cudaStream_t st) {
+                           int chunk_rays, const uint32_t *mask_words, const int32_t *block_offsets, cudaStream_t st) {
   unsigned blocks = (unsigned)((n_rays + 7) / 8);
   PeerScatter ps{};
   if (peers) {
@@ -1039,10 +1090,10 @@ int launch_composite_fused(const float *raw, const float *near, const float *far
   }
   if (S == 64)
     composite_kernel<2><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, near, far, t_vals, n_rays, white_bkgd, rgb_map, acc_map,
-                                                depth_map, nullptr, nullptr, ps);
+                                                depth_map, nullptr, nullptr, ps, mask_words, block_offsets);
   else
     composite_kernel<1><<<blocks, 256, 0, st>>>((const float4 *)raw, z_vals, near, far, t_vals, n_rays, white_bkgd, rgb_map, acc_map,
-                                                depth_map, nullptr, nullptr, ps);
+                                                depth_map, nullptr, nullptr, ps, mask_words, block_offsets);
   ANI_LAUNCHED();
   return ANINERF_OK;
 }

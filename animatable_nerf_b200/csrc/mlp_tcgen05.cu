@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                   if (args.sigma_masked_out) args.sigma_masked_out[o] = sg;
                   float al = 1.0f - expf(-fmaxf(sg, 0.f) * __ldg(args.dists + o));
                   float4 rv = make_float4(1.0f / (1.0f + expf(-rgb[0])), 1.0f / (1.0f + expf(-rgb[1])), 1.0f / (1.0f + expf(-rgb[2])), al);
-                  reinterpret_cast<float4 *>(args.raw_out)[__ldg(args.index + o)] = rv;
+                  reinterpret_cast<float4 *>(args.raw_out)[args.index ? (int64_t)__ldg(args.index + o) : o] = rv;   // dense scatter, or compact rows
                 }
               }
             }

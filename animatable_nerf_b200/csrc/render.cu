@@ -22,7 +22,7 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
                      const aninerf_silhouettes *sil, cudaStream_t st);
 int launch_composite_fused(const float *raw, const float *near, const float *far, const float *t_vals, const float *z_vals, int64_t n_rays,
                            int S, int white_bkgd, float *rgb_map, float *acc_map, float *depth_map, const aninerf_peer_gather *peers,
-                           int chunk_rays, cudaStream_t st);
+                           int chunk_rays, const uint32_t *mask_words, const int32_t *block_offsets, cudaStream_t st);
 int launch_mask_points(const float *wpts, int64_t n, const float *R, const float *Th, const float *bounds, const int32_t dims[3],
                        const float *dist_plane, float norm_th, int64_t chunk_pts, uint8_t *mask, unsigned long long *chunk_argmin,
                        float *ppts, cudaStream_t st);
@@ -91,6 +91,7 @@ struct RenderScratch {
   FrontEndBuffers fb;
   int32_t *index;
   float *ppts, *viewdir, *dists, *tpts, *z_vals;
+  float *raw_c;      // render-only: compact (n',4) rows of the active samples instead of the caller's dense raw
 };
 
 static int64_t carve_render(Carver &c, int64_t n_rays, int S, int want_bw, int64_t pv, int64_t tv, RenderScratch &s) {
@@ -111,6 +112,7 @@ static int64_t carve_render(Carver &c, int64_t n_rays, int S, int want_bw, int64
   s.dists = c.take<float>(n);
   s.tpts = c.take<float>(n * 3);
   s.z_vals = c.take<float>(n);
+  s.raw_c = c.take<float>(want_bw ? 0 : n * 4);
   return c.off;
 }
 
@@ -169,7 +171,8 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
                             int64_t workspace_bytes, void *stream) {
   ANI_CHECK_ARG(net && fr && pr && out && ray_o && ray_d && near && far && t_vals && workspace && n_rays >= 0);
   ANI_CHECK_ARG(fr->A && fr->R && fr->Th && fr->pbw && fr->pbounds && fr->tbounds);
-  ANI_CHECK_ARG(out->rgb_map && out->acc_map && out->depth_map && out->raw && out->n_active);
+  ANI_CHECK_ARG(out->rgb_map && out->acc_map && out->depth_map && out->n_active);
+  ANI_CHECK_ARG(out->raw || !pr->want_bw);     // the dense raw buffer is an output of the training contract only
   const int S = pr->n_samples;
   ANI_CHECK_ARG(S == 32 || S == 64);
   ANI_CHECK_ARG(pr->chunk_rays > 0 && ((int64_t)pr->chunk_rays * S) % 2048 == 0);
@@ -194,7 +197,8 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
     if ((rc = launch_split_volume(fr->pbw, fr->pbw_dims, s.w24_p, s.dist_p, st))) return rc;
     if (pr->want_bw && (rc = launch_split_volume(fr->tbw, fr->tbw_dims, s.w24_t, s.dist_t, st))) return rc;
   }
-  {
+  const bool dense = out->raw != nullptr;
+  if (dense) {
     StageTimer t(ST_CLEAR, st);
     ANI_CUDA(cudaMemsetAsync(out->raw, 0, n * 16, st));
   }
@@ -229,8 +233,8 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
   // 4. canonical NeRF field + tail of Network.forward, scattered into the dense raw buffer
   {
     StageTimer t(ST_NERF, st);
-    if ((rc = nerf_forward_impl(net, nerf_latent, fr->latent_index_dev, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds, index,
-                                out->raw, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st)))
+    if ((rc = nerf_forward_impl(net, nerf_latent, fr->latent_index_dev, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds,
+                                dense ? index : nullptr, dense ? out->raw : s.raw_c, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st)))
       return rc;
   }
   // 5. compositing
@@ -240,8 +244,8 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
     if ((rc = aninerf_sample_points(ray_o, ray_d, near, far, t_vals, t_rand, n_rays, S, nullptr, s.z_vals, nullptr, stream))) return rc;
     z = s.z_vals;
   }
-  return launch_composite_fused(out->raw, near, far, t_vals, z, n_rays, S, pr->white_bkgd, out->rgb_map, out->acc_map, out->depth_map, peers,
-                                pr->chunk_rays, st);
+  return launch_composite_fused(dense ? out->raw : s.raw_c, near, far, t_vals, z, n_rays, S, pr->white_bkgd, out->rgb_map, out->acc_map,
+                                out->depth_map, peers, pr->chunk_rays, dense ? nullptr : s.fb.mask_words, dense ? nullptr : s.fb.block_offsets, st);
 }
 
 extern "C" {

@@ -56,7 +56,7 @@ class Renderer:
 
     # ---------------------------------------------------------------------------------------
     @torch.no_grad()
-    def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None, peers=None):
+    def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None, peers=None, keep_raw=False):
         """The fused path, results left on the device.  Returns a dict with rgb_map/acc_map/depth_map
         (and raw, n_active, pbw_all/tbw_all/sigma_masked/chunk_offsets when want_bw).
         silhouettes: (_lib.Silhouettes, keep-alive) from tpose_renderer_mmsk -- cull the samples first.
@@ -81,9 +81,11 @@ class Renderer:
         n_chunks = (R + _lib.CHUNK_RAYS - 1) // _lib.CHUNK_RAYS
         out = {
             'rgb_map': torch.empty(R, 3, device=dev), 'acc_map': torch.empty(R, device=dev), 'depth_map': torch.empty(R, device=dev),
-            'raw': torch.empty(n, 4, device=dev), 'n_active': torch.zeros(1, dtype=torch.int32, device=dev),
+'n_active': torch.zeros(1, dtype=torch.int32, device=dev),
             'chunk_offsets': torch.zeros(n_chunks + 1, dtype=torch.int32, device=dev),
         }
+        if want_bw or keep_raw:
+            out['raw'] = torch.empty(n, 4, device=dev)     # dense (n,4): a training-contract output; render-only composites the compact rows
         if want_bw:
             out['pbw_all'] = torch.empty(n, 24, device=dev)
             out['tbw_all'] = torch.empty(n, 24, device=dev)

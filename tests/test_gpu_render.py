@@ -111,6 +111,13 @@ def test_render_only_mode_and_edge_sizes(dev):
         sub = {k: (v[:, :n] if k in ('ray_o', 'ray_d', 'near', 'far', 'occupancy') else v) for k, v in batch.items()}
         ref = O.render(sd, sub, O.OracleCfg(perturb=0.))
         _check_maps(r.render(to_device(sub, dev)), ref)
+    # render-only composites the compact active rows (no dense (n,4) buffer): bit-identical to compositing the dense raw
+    b = to_device(batch, dev)
+    compact = r.render_device(b, want_bw=False)
+    dense = r.render_device(b, want_bw=False, keep_raw=True)
+    assert 'raw' not in compact and 'raw' in dense
+    for k in ('rgb_map', 'acc_map', 'depth_map'):
+        assert torch.equal(compact[k], dense[k]), k
 
 
 def test_chunk_with_no_active_sample_forces_argmin(dev):
