@@ -64,8 +64,16 @@ __device__ __forceinline__ void stage_operand(uint8_t *hi, uint8_t *lo, const fl
     const int kg = row_contig ? t / ROWS : t % (G_KC / 8);
     const int r = r0 + row, k = k0 + kg * 8;
     float x[8];
+    const float *src = X + (long long)r * rs + (long long)k * ks;
+    if (ks == 1 && r < R && k + 8 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      // K-contiguous, 16-byte aligned, fully inside: two float4 loads
+      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src)), v1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+      x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = (r < R && k + j < K) ? __ldg(X + (long long)r * rs + (long long)(k + j) * ks) : 0.f;
+      for (int j = 0; j < 8; ++j) x[j] = (r < R && k + j < K) ? __ldg(src + (long long)j * ks) : 0.f;
+    }
     uint4 h, l;
     h.x = pack_bf16(x[0], x[1]);
     h.y = pack_bf16(x[2], x[3]);
@@ -159,19 +167,60 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_cons
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
       if (m < g.M) {
+        float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c + j;
-          if (n < g.N) {
-            float x = __uint_as_float(v[j]);
-            if (!split) {
-              if (g.bias) x += __ldg(g.bias + n);
-              if (g.accumulate) x += out[(long long)m * ldo + n];
-              if (g.relu) x = fmaxf(x, 0.f);
-              if (g.mask) x = __ldg(g.mask + (long long)m * g.ldm + n) > 0.f ? x : 0.f;
-            }
-            out[(long long)m * ldo + n] = x;
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        float *dst = out + (long long)m * ldo + n0 + c;
+        const bool full = n0 + c + 32 <= g.N;
+        const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (!split) {
+          if (g.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || n0 + c + j < g.N) x[j] += __ldg(g.bias + n0 + c + j);
           }
+          if (g.accumulate) {
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 o = reinterpret_cast<const float4 *>(dst)[q];
+                x[4 * q] += o.x; x[4 * q + 1] += o.y; x[4 * q + 2] += o.z; x[4 * q + 3] += o.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || n0 + c + j < g.N) x[j] += dst[j];
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          if (g.mask) {
+            const float *mk = g.mask + (long long)m * g.ldm + n0 + c;
+            if (full && ((reinterpret_cast<uintptr_t>(mk) & 15) == 0)) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 o = __ldg(reinterpret_cast<const float4 *>(mk) + q);
+                x[4 * q] = o.x > 0.f ? x[4 * q] : 0.f;
+                x[4 * q + 1] = o.y > 0.f ? x[4 * q + 1] : 0.f;
+                x[4 * q + 2] = o.z > 0.f ? x[4 * q + 2] : 0.f;
+                x[4 * q + 3] = o.w > 0.f ? x[4 * q + 3] : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || n0 + c + j < g.N) x[j] = __ldg(mk + j) > 0.f ? x[j] : 0.f;
+            }
+          }
+        }
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) reinterpret_cast<float4 *>(dst)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + c + j < g.N) dst[j] = x[j];
         }
       }
     }
@@ -286,7 +335,12 @@ int aninerf_gemm_x3(const aninerf_gemm *p, void *workspace, int64_t workspace_by
     g.partial = (float *)workspace;
   }
   int rc;
-  const int bn = p->N <= 32 ? 32 : p->N <= 64 ? 64 : p->N <= 128 ? 128 : 256;
+  // output tile width: the widest tile that still yields ~one CTA per SM pair (small training batches have few 128-row tiles)
+  int bn = p->N <= 32 ? 32 : p->N <= 64 ? 64 : p->N <= 128 ? 128 : 256;
+  {
+    const long long m_tiles = (p->M + G_BM - 1) / G_BM;
+    while (bn > 64 && m_tiles * ((p->N + bn - 1) / bn) * splits < 96) bn /= 2;
+  }
   if (splits > 1) {
     // grid.z > 1 selects the partial-buffer path inside the kernel
     rc = bn == 32 ? launch_gemm<32>(g, splits, st) : bn == 64 ? launch_gemm<64>(g, splits, st) : bn == 128 ? launch_gemm<128>(g, splits, st)

@@ -75,7 +75,7 @@ def gemm(segs, out: torch.Tensor, bias=None, relu=False, relu_mask=None, accumul
 
 def split_for(k: int) -> int:
     """split-K factor of a weight-gradient product reducing over k samples"""
-    return max(1, min(64, (k + 511) // 512))
+    return max(1, min(64, k // 128))
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor, accumulate=False):
