@@ -30,20 +30,25 @@ import torch  # noqa: E402
 
 FLOP_BW = 2 * 562688        # algorithmic FLOP per active sample, blend-weight MLP
 FLOP_NERF = 2 * 691712      # canonical NeRF MLP (unfolded layer shapes)
+# what the kernels EXECUTE per active sample: latent codes folded into biases (BW: 497 152 MAC), three bf16 passes for the
+# blend-weight field; NeRF: feature_fc o latent_fc o view_fc folded (491 008 + 256 + 283*128 + 384 MAC), one pass
+EXEC_FLOP_BW = 2 * 497152 * 3
+EXEC_FLOP_NERF = 2 * (491008 + 256 + 283 * 128 + 384)
 METRIC = 'samples/s (aninerf_313 1024x1024 frame render; ms/frame = ms_per_step)'
 WORKLOAD = 'aninerf_313 full 1024x1024 frame render (inverse LBS + canonical NeRF MLP + compositing), synthetic pose'
 CPU_SAMPLE_RAYS = 1024      # BASELINE config 1: 1024 rays x 64 samples on the CPU
 
 
-def ncu_traffic(kernel_prefix):
-    """DRAM read+write bytes per launch of a kernel from the newest committed ncu --set full summary (profiles/rNN_traffic.json)."""
+def ncu_traffic(kernel_prefix, key='dram_read_plus_write'):
+    """DRAM read+write bytes per launch (or tensor-pipe active %) of a kernel from the newest committed ncu --set full summary
+    (profiles/rNN_traffic.json, written by tools/ncu_summarize.py)."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))
     if not files:
         return None
     try:
         with open(files[-1]) as f:
-            t = json.load(f)['dram_read_plus_write']
+            t = json.load(f)[key]
         for k, v in t.items():
             if k.startswith(kernel_prefix):
                 return v
@@ -467,6 +472,10 @@ def run_b200(args):
         'traffic': ncu_traffic('mlp_kernel<3, 0' if dom == 'bw_field_posed' else 'mlp_kernel<1, 1'), 'traffic_unit': 'DRAM bytes per launch (ncu --set full, profiles/)',
         'peak_source': pk['source'] + ' (sustained bf16: kernel timed inside the step)',
         'algorithmic_flop_per_active_sample': cand[dom], 'active_samples_per_launch': n_active, 'launch_ms': stage_ms[dom],
+        'executed': {'note': 'tensor-core FLOP the kernel issues (bf16x3 = 3 passes, folded layer shapes); frac of the sustained cuBLAS bf16 rate',
+                     'tflops': n_active * (EXEC_FLOP_BW if dom == 'bw_field_posed' else EXEC_FLOP_NERF) / (stage_ms[dom] * 1e-3) / 1e12,
+                     'frac': n_active * (EXEC_FLOP_BW if dom == 'bw_field_posed' else EXEC_FLOP_NERF) / (stage_ms[dom] * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+                     'tensor_pipe_active_pct_ncu': ncu_traffic('mlp_kernel<3, 0' if dom == 'bw_field_posed' else 'mlp_kernel<1, 1', 'tensor_pipe_active_pct')},
         'both_mlps': {'tflops': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 if mlp_ms else None,
                       'frac': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'] if mlp_ms else None},
     }

@@ -88,12 +88,13 @@ if os.path.exists(rep):
     def to_bytes(v, u):
         v = float(v.replace(',', ''))
         return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
-    traffic = {}
+    traffic, tensor = {}, {}
     for r in rows[2:]:
         name = r[col['Kernel Name']]
         name = (name[5:] if name.startswith('void ') else name).split('(')[0]
+        tensor[name] = float(r[col['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']].replace(',', ''))
         traffic[name] = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) + \
             to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
     json.dump({'source': f'ncu --set full, gpurun_out/prof_{tag}.ncu-rep, bench.py --steps 3 --warmup 3 --no-cpu', 'unit': 'bytes per launch',
-               'dram_read_plus_write': traffic}, open(os.path.join(out, f'r{rnd}_traffic.json'), 'w'), indent=1)
+               'dram_read_plus_write': traffic, 'tensor_pipe_active_pct': tensor}, open(os.path.join(out, f'r{rnd}_traffic.json'), 'w'), indent=1)
     print('wrote full summary,', len(rows) - 2, 'kernels')
