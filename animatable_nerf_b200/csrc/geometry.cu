@@ -698,6 +698,66 @@ __global__ void __launch_bounds__(256) mask_kernel(SampleSetup p, const float *_
   }
 }
 
+// ONE block after the mask pass: (1) a chunk without active sample gets its argmin(pnorm) sample forced on
+// (tpose_nerf_network.py:154), (2) exclusive scan of the per-block counts -> compacted offsets and n_active, (3) per-chunk start
+// rows.  (Three single-block launches before; their fixed ~20 us is a visible share of a ray-tiled frame at 8 GPUs.)
+__global__ void __launch_bounds__(1024) finalize_mask_kernel(int64_t n_chunks, int64_t blocks_per_chunk, int64_t n_blocks, int64_t chunk_samples,
+                                                             const unsigned long long *__restrict__ chunk_argmin, uint32_t *__restrict__ mask_words,
+                                                             int32_t *__restrict__ block_counts, int32_t *__restrict__ block_offsets,
+                                                             int32_t *__restrict__ total, int32_t *__restrict__ chunk_offsets) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (1) one warp per chunk
+  for (int64_t c = warp; c < n_chunks; c += 32) {
+    const int64_t b0 = c * blocks_per_chunk, b1 = min(n_blocks, b0 + blocks_per_chunk);
+    int t = 0;
+    for (int64_t b = b0 + lane; b < b1; b += 32) t += block_counts[b];
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && t == 0 && chunk_argmin[c] != ~0ull) {   // ~0: silhouette culling left the chunk empty, the network is not called
+      const int64_t i = c * chunk_samples + (int64_t)(chunk_argmin[c] & 0xffffffffull);
+      mask_words[i / 32] |= 1u << (i % 32);
+      block_counts[i / MB] += 1;
+    }
+  }
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  // (2) exclusive scan of the block counts
+  for (int64_t base = 0; base < n_blocks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int v = i < n_blocks ? block_counts[i] : 0;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ws = warp_sums[threadIdx.x];
+      int winc = ws;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (threadIdx.x >= o) winc += t;
+      }
+      warp_sums[threadIdx.x] = winc - ws;
+    }
+    __syncthreads();
+    const int excl = carry + warp_sums[warp] + inc - v;
+    if (i < n_blocks) block_offsets[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+  // (3) chunk c starts at the offset of its first block
+  if (chunk_offsets)
+    for (int64_t c = threadIdx.x; c <= n_chunks; c += 1024) {
+      const int64_t b = c * blocks_per_chunk;
+      chunk_offsets[c] = b < n_blocks ? block_offsets[b] : carry;
+    }
+}
+
 // one thread per chunk: if a chunk has no active sample, force its argmin(pnorm) sample on
 // (tpose_nerf_network.py:154).  Also emits per-chunk totals.
 __global__ void force_argmin_kernel(int64_t n_chunks, int64_t blocks_per_chunk, int64_t n_blocks, int64_t chunk_samples,
@@ -1062,16 +1122,9 @@ int launch_front_end(const float *ray_o, const float *ray_d, const float *near, 
   ANI_CUDA(cudaMemsetAsync(fb.chunk_argmin, 0xff, n_chunks * 8, st));
   mask_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(p, dist_plane, chunk_samples, fb.mask_words, fb.block_counts, fb.chunk_argmin);
   ANI_LAUNCHED();
-  force_argmin_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(n_chunks, blocks_per_chunk, n_blocks, chunk_samples,
-                                                                          fb.chunk_argmin, fb.mask_words, fb.block_counts);
+  finalize_mask_kernel<<<1, 1024, 0, st>>>(n_chunks, blocks_per_chunk, n_blocks, chunk_samples, fb.chunk_argmin, fb.mask_words, fb.block_counts,
+                                           fb.block_offsets, n_active, chunk_offsets);
   ANI_LAUNCHED();
-  scan_counts_kernel<<<1, 1024, 0, st>>>(fb.block_counts, n_blocks, fb.block_offsets, n_active);
-  ANI_LAUNCHED();
-  if (chunk_offsets) {
-    chunk_offsets_kernel<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, st>>>(n_chunks, blocks_per_chunk, n_blocks, fb.block_offsets,
-                                                                                 n_active, chunk_offsets);
-    ANI_LAUNCHED();
-  }
   compact_samples_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(p, fb.mask_words, fb.block_offsets, index, ppts, viewdir, dists);
   ANI_LAUNCHED();
   return ANINERF_OK;
