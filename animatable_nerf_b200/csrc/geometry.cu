@@ -758,34 +758,6 @@ __global__ void __launch_bounds__(1024) finalize_mask_kernel(int64_t n_chunks, i
     }
 }
 
-// one thread per chunk: if a chunk has no active sample, force its argmin(pnorm) sample on
-// (tpose_nerf_network.py:154).  Also emits per-chunk totals.
-__global__ void force_argmin_kernel(int64_t n_chunks, int64_t blocks_per_chunk, int64_t n_blocks, int64_t chunk_samples,
-                                    const unsigned long long *__restrict__ chunk_argmin, uint32_t *__restrict__ mask_words,
-                                    int32_t *__restrict__ block_counts) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  int64_t b0 = c * blocks_per_chunk, b1 = min(n_blocks, b0 + blocks_per_chunk);
-  int tot = 0;
-  for (int64_t b = b0; b < b1; ++b) tot += block_counts[b];
-  if (tot == 0 && chunk_argmin[c] != ~0ull) {   // ~0: silhouette culling left the chunk empty, the network is not called
-    int64_t local = (int64_t)(chunk_argmin[c] & 0xffffffffull);
-    int64_t i = c * chunk_samples + local;
-    mask_words[i / 32] |= 1u << (i % 32);
-    block_counts[i / MB] += 1;
-  }
-}
-
-// chunk_offsets[c] = compacted start row of chunk c (c = 0..n_chunks), from the scanned block offsets
-__global__ void chunk_offsets_kernel(int64_t n_chunks, int64_t blocks_per_chunk, int64_t n_blocks,
-                                     const int32_t *__restrict__ block_offsets, const int32_t *__restrict__ total,
-                                     int32_t *__restrict__ chunk_offsets) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > n_chunks) return;
-  int64_t b = c * blocks_per_chunk;
-  chunk_offsets[c] = b < n_blocks ? block_offsets[b] : *total;
-}
-
 // scatter the active samples in ascending index order: index, pose point, view direction, dist
 __global__ void __launch_bounds__(256) compact_samples_kernel(SampleSetup p, const uint32_t *__restrict__ mask_words,
                                                               const int32_t *__restrict__ block_offsets, int32_t *__restrict__ index,

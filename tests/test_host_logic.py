@@ -150,3 +150,62 @@ def test_circular_camera_path_is_a_closed_orbit_of_rigid_transforms():
         pos = np.linalg.inv(m)[:3, 3]
         look = np.linalg.inv(m)[:3, 2]                    # camera z axis in the world
         assert np.dot(look, centre - pos) > 0               # every camera looks towards the orbit's inside
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    """The reference's checkpoint dict ({net, optim, scheduler, recorder, epoch}, <epoch>.pth / latest.pth,
+    lib/utils/net_utils.py:288-396) written and read back; `only=` keeps a sub-field as load_network does."""
+    import torch
+    from animatable_nerf_b200 import checkpoint, config, synthetic
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    cfg = config.make_cfg(aninerf_animation=True, num_eval_frame=5)
+    net = Network(cfg)
+    net.load_state_dict(synthetic.make_state_dict(seed=3, num_eval_frame=5))
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, 0.9)
+    d = str(tmp_path / 'model')
+    for ep in (3, 7):
+        checkpoint.save_model(net, opt, sched, None, d, ep)
+    checkpoint.save_model(net, opt, sched, None, d, 9, last=True)
+    state = torch.load(d + '/7.pth', map_location='cpu')
+    assert set(state) == {'net', 'optim', 'scheduler', 'recorder', 'epoch'} and state['epoch'] == 7
+    assert set(state['net']) == set(net.state_dict())
+    net2 = Network(cfg)
+    opt2 = torch.optim.Adam(net2.parameters(), lr=1e-3)
+    assert checkpoint.load_model(net2, opt2, torch.optim.lr_scheduler.ExponentialLR(opt2, 0.9), None, d) == 10      # latest.pth wins
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    net3 = Network(cfg)
+    before = net3.tpose_human.alpha_fc.weight.clone()
+    assert checkpoint.load_network(net3, d, epoch=3, only=['novel_pose_bw']) == 4
+    assert torch.equal(net3.novel_pose_bw.bw_fc.weight, net.novel_pose_bw.bw_fc.weight) and torch.equal(net3.tpose_human.alpha_fc.weight, before)
+    assert checkpoint.load_network(net3, str(tmp_path / 'missing')) == 0
+
+
+def test_load_frame_from_sequence_files(tmp_path):
+    """A processed-sequence directory (vertices / params / bweights / tbw / tvertices / joints / parents .npy,
+    lib/datasets/tpose_dataset.py:125-161) read back into the frame dict the renderer consumes."""
+    import numpy as np
+    from animatable_nerf_b200 import checkpoint, host_geometry, synthetic
+    frame = synthetic.make_frame(voxel=0.1)
+    tverts, w, J = synthetic.make_body(1)
+    root, lbs = tmp_path / 'seq', tmp_path / 'seq' / 'lbs'
+    for p in (root / 'new_vertices', root / 'new_params', lbs / 'bweights'):
+        p.mkdir(parents=True)
+    rng = np.random.RandomState(2)
+    poses = rng.normal(0, 0.2, (24, 3))
+    poses[0] = 0
+    Rh = rng.normal(0, 0.3, 3)
+    np.save(root / 'new_vertices' / '4.npy', frame['wverts'])
+    np.save(root / 'new_params' / '4.npy', {'Rh': Rh[None], 'Th': frame['Th'], 'poses': poses.reshape(1, 72), 'shapes': np.zeros((1, 10))},
+            allow_pickle=True)
+    np.save(lbs / 'bweights' / '4.npy', frame['pbw'])
+    np.save(lbs / 'tbw.npy', frame['tbw'])
+    np.save(lbs / 'tvertices.npy', tverts)
+    np.save(lbs / 'joints.npy', J)
+    np.save(lbs / 'parents.npy', host_geometry.SMPL_PARENTS)
+    got = checkpoint.load_frame(str(root), str(lbs), 4, latent_index=2)
+    assert set(synthetic.FRAME_KEYS) <= set(got)
+    for k in ('A', 'R', 'pbw', 'tbw', 'wbounds', 'tbounds'):
+        assert np.allclose(got[k], frame[k], atol=1e-6), k
+    assert np.allclose(got['pbounds'], frame['pbounds'], atol=1e-5)
+    assert got['Th'].shape == (1, 3) and int(got['latent_index']) == 2
