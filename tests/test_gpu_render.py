@@ -231,3 +231,40 @@ def test_mmsk_chunk_without_survivors_evaluates_nothing(dev):
     assert float(dev_out['acc_map'].abs().max()) == 0.0 and float(dev_out['rgb_map'].abs().max()) == 0.0
     ref = O.render_mmsk(sd, mb, O.OracleCfg(perturb=0.))
     _check_maps({k: dev_out[k][None] for k in ('rgb_map', 'acc_map', 'depth_map')}, ref)
+
+
+def test_full_frame_properties_at_baseline_size(dev):
+    """BASELINE config 2 (1024x1024, ~243 k rays x 64): too big for the oracle, so size-independent properties --
+    (1) ray-tile invariance: the chunks 0,2,4,.. and 1,3,5,.. rendered separately and re-interleaved equal the whole-frame
+        render bit for bit (what the N-GPU path relies on);
+    (2) compact compositing == dense compositing bit for bit; the dense raw is zero exactly off the active set;
+    (3) ranges: acc in [0,1], rgb in [0,1], depth within [0, max far]; rays whose 64 samples are all inactive composite to 0."""
+    from animatable_nerf_b200 import frontend, ray_tiles, synthetic
+    frame = synthetic.make_frame(pose_seed=2, body_seed=1, voxel=0.025)
+    K, R, T = synthetic.make_camera(frame, 1024, 1024)
+    ro, rd, near, far, mask = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    n = ro.shape[0]
+    assert 200_000 < n < 300_000
+    sd = synthetic.make_state_dict(seed=0)
+    r = _renderer(dev, sd, b200_render_only=True)
+    full = synthetic.make_render_batch(frame, ro, rd, near, far, device=dev)
+    whole = r.render_device(full, want_bw=False, keep_raw=True)
+    maps = torch.cat([whole['rgb_map'], whole['acc_map'][:, None], whole['depth_map'][:, None]], dim=1)
+    tiled = torch.empty_like(maps)
+    for rank in range(2):
+        idx = ray_tiles.shard_indices(n, rank, 2, device=dev)
+        part = r.render_device(ray_tiles.shard_batch(full, rank, 2), want_bw=False)
+        tiled[idx] = torch.cat([part['rgb_map'], part['acc_map'][:, None], part['depth_map'][:, None]], dim=1)
+    assert torch.equal(tiled, maps)
+    compact = r.render_device(full, want_bw=False)
+    for k in ('rgb_map', 'acc_map', 'depth_map'):
+        assert torch.equal(compact[k], whole[k]), k
+    na = int(whole['n_active'].item())
+    raw = whole['raw'].view(n, 64, 4)
+    assert int((raw[..., :3] != 0).any(-1).sum()) == na            # sigmoid(rgb) > 0 exactly on the active samples
+    acc, rgb, depth = whole['acc_map'], whole['rgb_map'], whole['depth_map']
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-5
+    assert float(depth.min()) >= 0.0 and float(depth.max()) <= float(far.max()) * (1.0 + 1e-5)
+    empty = ~(raw[..., :3] != 0).any(-1).any(-1)
+    assert float(acc[empty].abs().max()) == 0.0 and float(rgb[empty].abs().max()) == 0.0
