@@ -42,6 +42,7 @@ class AnimationStep:
             raise _lib.AninerfError('the network has no novel_pose_bw field (cfg.aninerf_animation must be True)')
         _lib.require_cuda(wpts, 'wpts')
         dev = wpts.device
+        T.begin_step(dev)
         wpts, tpts = _lib.f32c(wpts.reshape(-1, 3)), _lib.f32c(tpts.reshape(-1, 3))
         G = _Grads(net)
         A = _lib.f32c(batch['A'].reshape(24, 4, 4))
@@ -141,6 +142,7 @@ class AnimationStep:
         ret = {'pbw0': pbw[sel0.bool()]}
         stats = {'bw_loss0': losses[0], 'bw_loss1': losses[1], 'loss': losses[0] + losses[1]}
         self._keep = (A, pvol, tvol, pb, tb, Rm, Th, wpts, tpts)
+        T.end_step(dev)
         return ret, stats, G
 
 

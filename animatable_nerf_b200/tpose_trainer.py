@@ -122,6 +122,137 @@ class _Trunk:
         return d_pe
 
 
+class _PlannedTrunk:
+    """`_Trunk` with everything static: activations live in buffers sized for `m_max` rows, and every product of the forward /
+    backward pass is a prebuilt `aninerf_gemm` descriptor -- per call only the row count (M, or K and the split factor of a
+    weight gradient) is patched and the library entry invoked.  ~35 launches per pass cost ~3 us of host time each instead of
+    ~16 us (descriptor construction, operand views, allocations), which is what bounds a 1024-ray training iteration."""
+
+    def __init__(self, sd, prefix, lat_cols, grads, m_max, dev, pe=None, d_pe=None):
+        self.W = [_w2(sd[f'{prefix}.{i}.weight']) for i in range(8)]
+        self.b = [sd[f'{prefix}.{i}.bias'].detach() for i in range(8)]
+        self.gW = [grads.w(f'{prefix}.{i}.weight') for i in range(8)]
+        self.gb = [grads.views[f'{prefix}.{i}.bias'] for i in range(8)]
+        self.lat_cols, self.hid0, self.m_max, self.dev = lat_cols, 63 + lat_cols, m_max, dev
+        z = lambda *sh: torch.zeros(*sh, device=dev)   # noqa: E731
+        self.pe = pe if pe is not None else z(m_max, 64)
+        self.d_pe = d_pe
+        self.H = [None] + [z(m_max, 256) for _ in range(8)]
+        self.dz = [z(m_max, 256), z(m_max, 256)]          # dz[0] = the incoming gradient of layer 7's pre-activation
+        self.lat, self.g_lat = z(1, 128), z(1, 128)
+        self.beff = {0: z(1, 256), 5: z(1, 256)}
+        self.db = z(1, 256)
+        self._keep = []
+        self.fwd = self._plan_forward()
+        self.bwd = {}
+
+    # -- descriptors -----------------------------------------------------------------------------------------------------
+    def _gemm(self, segs, out, bias=None, relu=False, relu_mask=None, accumulate=False, dyn=0):
+        g = _lib.Gemm()
+        g.n_seg = len(segs)
+        for i, (a, b) in enumerate(segs):
+            sg = g.seg[i]
+            sg.A, sg.a_row_stride, sg.a_k_stride = a.ptr, a.rs, a.ks
+            sg.B, sg.b_row_stride, sg.b_k_stride = b.ptr, b.rs, b.ks
+            sg.K = a.k
+        g.M, g.N, g.C, g.ldc = out.shape[0], out.shape[1], out.data_ptr(), out.stride(0)
+        if bias is not None:
+            g.bias = bias.data_ptr()
+        if relu_mask is not None:
+            g.relu_mask, g.ld_mask = relu_mask.data_ptr(), relu_mask.stride(0)
+        g.relu, g.accumulate, g.split_k = int(relu), int(accumulate), 1
+        self._keep.append((segs, out, bias, relu_mask))
+        return (0, g, C.byref(g), dyn)            # dyn: 0 static, 1 patch M, 2 patch K of segment 0 (+ split-K)
+
+    def _colsum(self, x, out, accumulate):
+        self._keep.append((x, out))
+        return (1, (x.data_ptr(), x.stride(0), x.shape[1], out.data_ptr(), int(accumulate)), None, 1)
+
+    def _plan_forward(self):
+        ops, H, pe = [], self.H, self.pe
+        for l in range(8):
+            bias = self.b[l]
+            if self.lat_cols and l in (0, 5):
+                bias = self.beff[l]
+                ops.append(self._gemm([(Op(self.lat), Op(self.W[l][:, 63:63 + self.lat_cols]))], bias, bias=self.b[l]))
+            if l == 0:
+                segs = [(Op(pe[:, :63]), Op(self.W[0][:, :63]))]
+            elif l == 5:
+                segs = [(Op(pe[:, :63]), Op(self.W[5][:, :63])), (Op(H[5]), Op(self.W[5][:, self.hid0:]))]
+            else:
+                segs = [(Op(H[l]), Op(self.W[l]))]
+            ops.append(self._gemm(segs, H[l + 1], bias=bias, relu=True, dyn=1))
+        return ops
+
+    def _plan_backward(self, want_dpe, wgrad):
+        ops, H, pe, dz = [], self.H, self.pe, self.dz
+        cur = 0
+        for l in range(7, -1, -1):
+            W, gW, dZ = self.W[l], self.gW[l], dz[cur]
+            if wgrad:
+                if l in (0, 5):
+                    ops.append(self._gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, dyn=2))
+                if l == 5:
+                    ops.append(self._gemm([(Op(dZ).T, Op(H[5]).T)], gW[:, self.hid0:], accumulate=True, dyn=2))
+                elif l != 0:
+                    ops.append(self._gemm([(Op(dZ).T, Op(H[l]).T)], gW, accumulate=True, dyn=2))
+                if self.lat_cols and l in (0, 5):
+                    Wl = W[:, 63:63 + self.lat_cols]
+                    ops.append(self._colsum(dZ, self.db, False))
+                    ops.append(self._colsum(dZ, self.gb[l], True))
+                    ops.append(self._gemm([(Op(self.db).T, Op(self.lat).T)], gW[:, 63:63 + self.lat_cols], accumulate=True))
+                    ops.append(self._gemm([(Op(self.db), Op(Wl).T)], self.g_lat, accumulate=(l == 0)))     # layer 5 comes first
+                else:
+                    ops.append(self._colsum(dZ, self.gb[l], True))
+            if want_dpe and l in (0, 5):
+                ops.append(self._gemm([(Op(dZ), Op(W[:, :63]).T)], self.d_pe[:, :63], accumulate=(l == 0), dyn=1))
+            if l > 0:
+                Wh = W[:, self.hid0:] if l == 5 else W
+                ops.append(self._gemm([(Op(dZ), Op(Wh).T)], dz[1 - cur], relu_mask=H[l], dyn=1))
+                cur = 1 - cur
+        return ops
+
+    # -- execution -------------------------------------------------------------------------------------------------------
+    def _run(self, ops, m):
+        L = _lib.lib()
+        gemm, colsum = L.aninerf_gemm_x3, L.aninerf_colsum
+        st = T._st(self.dev)
+        sk = T.split_for(m)
+        ws = T._ws.get(max(sk * 256 * 447 * 4, ((m + 255) // 256) * 256 * 4), self.dev)
+        wsp = _lib.ptr(ws)
+        for kind, a, ref, dyn in ops:
+            if kind == 0:
+                nbytes = 0
+                if dyn == 1:
+                    a.M = m
+                elif dyn == 2:
+                    a.seg[0].K = m
+                    a.split_k = sk
+                    nbytes = sk * a.M * a.N * 4 if sk > 1 else 0
+                rc = gemm(ref, wsp, nbytes, st)
+            else:
+                x, ld, n_cols, out, acc = a
+                rc = colsum(x, ld, m, n_cols, out, acc, wsp, ((m + 255) // 256) * n_cols * 4, st)
+            if rc:
+                _lib.check(rc)
+
+    def forward(self, m, lat):
+        """The PE of the m rows is in self.pe[:m]; returns H8 (view of the static buffer)."""
+        if self.lat_cols:
+            self.lat.copy_(lat)
+        self._run(self.fwd, m)
+        return self.H[8][:m]
+
+    def backward(self, m, g_lat_row, want_dpe, wgrad=True):
+        """self.dz[0][:m] holds the gradient of layer 7's pre-activation; the PE gradient lands in self.d_pe[:m]."""
+        key = (bool(want_dpe), bool(wgrad))
+        if key not in self.bwd:
+            self.bwd[key] = self._plan_backward(*key)
+        self._run(self.bwd[key], m)
+        if self.lat_cols and wgrad and g_lat_row is not None:
+            g_lat_row.add_(self.g_lat)
+
+
 class TrainStep:
     """Forward + backward of one training batch on the library's kernels; holds no state between calls except scratch."""
 
@@ -130,6 +261,20 @@ class TrainStep:
         self.cfg = cfg if cfg is not None else getattr(net, 'cfg', None) or config.global_cfg()
         self._renderer = Renderer(net, self.cfg)
         self._ws = None
+        self._plan = None
+
+    def _ensure_plan(self, n, dev, sd):
+        """Static state of the step: the flat gradient buffer and the three planned trunks (posed / canonical blend-weight
+        field, NeRF trunk), sized for n = n_rays * N_samples rows; rebuilt when the size, device or parameter storage changes."""
+        key = (n, str(dev), tuple(p.data_ptr() for p in sd.values()))
+        if self._plan is None or self._plan['key'] != key:
+            G = _Grads(self.net)
+            d_pe = torch.zeros(n, 64, device=dev)
+            tp = _PlannedTrunk(sd, 'bw_linears', 128, G, n, dev)
+            tc = _PlannedTrunk(sd, 'bw_linears', 128, G, n, dev, d_pe=d_pe)
+            tn = _PlannedTrunk(sd, 'tpose_human.pts_linears', 0, G, n, dev, pe=tc.pe, d_pe=d_pe)
+            self._plan = {'key': key, 'G': G, 'd_pe': d_pe, 'trunk_p': tp, 'trunk_c': tc, 'trunk_n': tn}
+        return self._plan
 
     def _workspace(self, nbytes, dev):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
@@ -148,6 +293,7 @@ class TrainStep:
         _lib.require_cuda(ray_o, "batch['ray_o']")
         dev = ray_o.device
         st = _lib.stream_ptr(dev)
+        T.begin_step(dev)
         R = ray_o.shape[1]
         S = int(config.get(cfg, 'N_samples'))
         n = R * S
@@ -176,7 +322,10 @@ class TrainStep:
         m = int(n_active.item())                      # the reference syncs here too (boolean indexing, tpose_nerf_network.py:155-157)
         index, ppts, viewdir, dists = index[:m], ppts_all[:m], vd_all[:m], dists_all[:m]
 
-        G = _Grads(net)
+        plan = self._ensure_plan(n, dev, sd)
+        G = plan['G']
+        G.flat.zero_()
+        trunk_p, trunk_c, trunk_n, d_pe_all = plan['trunk_p'], plan['trunk_c'], plan['trunk_n'], plan['d_pe']
         A = _lib.f32c(batch['A'].reshape(24, 4, 4))
         pvol, tvol = _lib.f32c(batch['pbw'][0]), _lib.f32c(batch['tbw'][0])
         pb, tb = _lib.f32c(batch['pbounds'].reshape(2, 3)), _lib.f32c(batch['tbounds'].reshape(2, 3))
@@ -188,24 +337,21 @@ class TrainStep:
             return torch.empty(*shape, device=dev)
 
         # ---- blend-weight field at the posed points + inverse LBS (tpose_nerf_network.py:79-100) ------------------------
-        pe_p = T.pe_forward(ppts, 10, e(m, 64))
-        trunk_p = _Trunk(sd, 'bw_linears', 128, G)
-        h8p = trunk_p.forward(pe_p, lat_p)
+        T.pe_forward(ppts, 10, trunk_p.pe[:m])
+        h8p = trunk_p.forward(m, lat_p)
         delta_p = T.gemm([(Op(h8p), Op(Wfc))], e(m, 24), bias=bfc)
         init_p = T.sample_volume(ppts, pvol, pb, e(m, 25))
         pbw = T.bw_softmax_forward(init_p, delta_p, e(m, 24))
         tpts = T.inverse_lbs(ppts, pbw, A, e(m, 3))
         # ---- blend-weight field at the canonical points, latent index 0 (:163-170) --------------------------------------
-        pe_c = T.pe_forward(tpts, 10, e(m, 64))
-        trunk_c = _Trunk(sd, 'bw_linears', 128, G)
-        h8c = trunk_c.forward(pe_c, lat_c)
+        T.pe_forward(tpts, 10, trunk_c.pe[:m])
+        h8c = trunk_c.forward(m, lat_c)
         delta_c = T.gemm([(Op(h8c), Op(Wfc))], e(m, 24), bias=bfc)
         init_t = T.sample_volume(tpts, tvol, tb, e(m, 25))
         tbw = T.bw_softmax_forward(init_t, delta_c, e(m, 24))
         # ---- canonical NeRF field (:252-275) ----------------------------------------------------------------------------
         p = 'tpose_human.'
-        trunk_n = _Trunk(sd, p + 'pts_linears', 0, G)
-        h8n = trunk_n.forward(pe_c, None)
+        h8n = trunk_n.forward(m, None)          # shares the PE(tpose) buffer of the canonical blend-weight trunk
         Wa, Wf, Wl, Wv, Wr = (_w2(sd[p + k + '.weight']) for k in ('alpha_fc', 'feature_fc', 'latent_fc', 'view_fc', 'rgb_fc'))
         ba, bf, bl, bv, br = (sd[p + k + '.bias'].detach() for k in ('alpha_fc', 'feature_fc', 'latent_fc', 'view_fc', 'rgb_fc'))
         sigma = T.gemm([(Op(h8n), Op(Wa))], e(m, 1), bias=ba)
@@ -264,10 +410,10 @@ class TrainStep:
         T.colsum(d_feat, gv[p + 'feature_fc.bias'], accumulate=True)
         T.gemm([(Op(d_sigma).T, Op(h8n).T)], gw(p + 'alpha_fc.weight'), accumulate=True, split_k=sk)
         T.colsum(d_sigma, gv[p + 'alpha_fc.bias'], accumulate=True)
-        dz = T.gemm([(Op(d_feat), Op(Wf).T)], e(m, 256))
+        dz = T.gemm([(Op(d_feat), Op(Wf).T)], trunk_n.dz[0][:m])
         T.gemm([(Op(d_sigma), Op(Wa).T)], dz, accumulate=True, relu_mask=h8n)
-        d_pe = torch.zeros(m, 64, device=dev)
-        trunk_n.backward(dz, None, d_pe)
+        d_pe = d_pe_all[:m]
+        trunk_n.backward(m, None, True)
         d_tpts = T.pe_backward(tpts, d_pe, 10, e(m, 3), False)
         # canonical blend-weight field
         d_delta, d_init = e(m, 24), e(m, 24)
@@ -275,9 +421,9 @@ class TrainStep:
         gWfc, gbfc = gw('bw_fc.weight'), gv['bw_fc.bias']
         T.gemm([(Op(d_delta).T, Op(h8c).T)], gWfc, accumulate=True, split_k=sk)
         T.colsum(d_delta, gbfc, accumulate=True)
-        dz = T.gemm([(Op(d_delta), Op(Wfc).T)], e(m, 256), relu_mask=h8c)
+        T.gemm([(Op(d_delta), Op(Wfc).T)], trunk_c.dz[0][:m], relu_mask=h8c)
         g_bw_lat = gv['bw_latent.weight']
-        trunk_c.backward(dz, g_bw_lat[0:1], d_pe)
+        trunk_c.backward(m, g_bw_lat[0:1], True)
         T.pe_backward(tpts, d_pe, 10, d_tpts, True)
         T.sample_volume_backward(tpts, tvol, tb, d_init, d_tpts, True)
         # inverse LBS: d tpose -> d pbw (added to the bw-loss gradient)
@@ -286,14 +432,15 @@ class TrainStep:
         T.bw_softmax_backward(init_p, pbw, d_pbw, d_delta, None)
         T.gemm([(Op(d_delta).T, Op(h8p).T)], gWfc, accumulate=True, split_k=sk)
         T.colsum(d_delta, gbfc, accumulate=True)
-        dz = T.gemm([(Op(d_delta), Op(Wfc).T)], e(m, 256), relu_mask=h8p)
-        trunk_p.backward(dz, g_bw_lat[latent_index + 1:latent_index + 2], None)
+        T.gemm([(Op(d_delta), Op(Wfc).T)], trunk_p.dz[0][:m], relu_mask=h8p)
+        trunk_p.backward(m, g_bw_lat[latent_index + 1:latent_index + 2], False)
 
         selb = sel.bool()
         ret = {'rgb_map': rgb_map.view(1, R, 3), 'acc_map': acc_map.view(1, R), 'depth_map': depth_map.view(1, R), 'raw': raw.view(1, n, 4),
                'pbw': pbw[selb].view(1, -1, 24), 'tbw': tbw[selb].view(1, -1, 24)}
         stats = {'bw_loss': losses[0], 'img_loss': losses[1], 'loss': losses[0] + losses[1]}
         self._keep = (keep, o, d, near, far, tr, A, pvol, tvol, pb, tb, rgb_gt, mask)
+        T.end_step(dev)
         return ret, stats, G
 
 
@@ -344,9 +491,11 @@ class NetworkWrapper(nn.Module):
 def allreduce_gradients(net, world_size: int, group=None):
     """Data-parallel gradient average (what DistributedDataParallel does in trainer.py:13-19) as ONE collective over a flat
     buffer: NCCL all-reduce(sum) of 1 274 652 floats, then 1/world."""
+    if world_size <= 1:
+        return
     import torch.distributed as dist
     params = [p for p in net.parameters() if p.grad is not None]
-    if world_size <= 1 or not params:
+    if not params:
         return
     flat = torch.cat([p.grad.reshape(-1) for p in params])
     dist.all_reduce(flat, group=group)

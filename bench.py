@@ -290,7 +290,7 @@ def other_configs(dev, frame, rank, world):
     w4 = NetworkWrapper(net4, cfg4)
     tb, t_rand = synthetic.make_train_batch(frame, ro.cpu().numpy(), rd.cpu().numpy(), near.cpu().numpy(), far.cpu().numpy(), n_rays=1024,
                                             ray_seed=3 + rank, device=dev)
-    opt = torch.optim.Adam(net4.parameters(), lr=5e-4)
+    opt = torch.optim.Adam(net4.parameters(), lr=5e-4, fused=True)      # lib/train/optimizer.py:12-27 (Adam, lr 5e-4); fused = one kernel
     L = None
     from animatable_nerf_b200 import _lib
     L = _lib.lib()
