@@ -268,3 +268,27 @@ def test_full_frame_properties_at_baseline_size(dev):
     assert float(depth.min()) >= 0.0 and float(depth.max()) <= float(far.max()) * (1.0 + 1e-5)
     empty = ~(raw[..., :3] != 0).any(-1).any(-1)
     assert float(acc[empty].abs().max()) == 0.0 and float(rgb[empty].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('pose_seed,voxel,azimuth,latent,white', [(5, 0.05, 0.9, 0, False), (9, 0.04, 2.4, 17, True), (13, 0.06, 4.0, 59, False)])
+def test_render_other_poses_views_and_backgrounds(dev, pose_seed, voxel, azimuth, latent, white):
+    """Different synthetic poses / volume resolutions / camera azimuths / latent codes, with and without cfg.white_bkgd, in both
+    the render-only (compact compositing) and the full-contract (dense raw) mode: active set bit-exact, maps within 2e-3."""
+    from animatable_nerf_b200 import synthetic
+    frame = synthetic.make_frame(pose_seed=pose_seed, body_seed=1, voxel=voxel, latent_index=latent)
+    K, R, T = synthetic.make_camera(frame, 112, 112, focal=120.0, azimuth=azimuth)
+    ro, rd, near, far, mask = O.get_rays_within_bounds(112, 112, K, R, T, frame['wbounds'])
+    assert ro.shape[0] > 2048                                        # more than one chunk, ragged tail
+    batch = synthetic.make_render_batch(frame, ro, rd, near, far)
+    sd = synthetic.make_state_dict(seed=pose_seed)
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0., white_bkgd=white), return_debug=True)
+    for render_only in (True, False):
+        r = _renderer(dev, sd, white_bkgd=white, b200_render_only=render_only)
+        dv = r.render_device(to_device(batch, dev))
+        assert int(dv['n_active'].item()) == int(ref['_debug']['pind'].sum())
+        _check_maps({k: dv[k].view(ref[k].shape) for k in ('rgb_map', 'acc_map', 'depth_map')}, ref)
+        if not render_only:
+            na = int(dv['n_active'].item())
+            assert np.array_equal(dv['active_index'][:na].cpu().numpy(), np.nonzero(ref['_debug']['pind'].numpy())[0].astype(np.int32))
+            assert float((dv['pbw_all'][:na].cpu() - ref['_debug']['pbw_all']).abs().max()) <= BW_TOL
+            assert float((dv['raw'].view(ref['raw'].shape).cpu() - ref['raw']).abs().max()) <= RGB_TOL
