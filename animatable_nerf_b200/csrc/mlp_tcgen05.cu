@@ -239,7 +239,10 @@ __device__ __forceinline__ void fast_corner(const float *gs, const int32_t dim[3
 // ------------------------------------------------------------------------------------------------
 constexpr int ROW_WARPS = 8;                       // two threads per row: each takes half of the columns
 constexpr int ROW_THREADS = ROW_WARPS * 32;        // 256
-constexpr int N_THREADS = ROW_THREADS + 96;        // + warp 8: weight producer, warps 9-10: MMA issue (one thread per tile slot) / TMEM alloc / relay
+// Threads of a CTA: ROW_THREADS per tile slot (NT = 2: each slot has its OWN eight epilogue warps, so the two slots' epilogues run
+// concurrently instead of queueing behind each other on the same threads), then one weight-producer warp and two warps for MMA
+// issue (one thread per tile slot) / TMEM alloc / relays.
+constexpr int n_threads(int nt) { return ROW_THREADS * nt + 96; }
 constexpr int XCHG_BYTES = TILE_M * 4 * 4;         // per-row exchange between the two column halves
 constexpr int PROD_LANES = 8;                      // producer lanes take turns issuing the bulk copies: one thread keeps only
                                                    // ~one copy in flight (20-28 B/cycle, tools/bench_stream.cu); several
@@ -270,7 +273,9 @@ struct Cfg {
 };
 
 template <int NPASS, bool NERF, int PAIR, int NT>
-__global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant__ MlpArgs args) {
+__global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_constant__ MlpArgs args) {
+  constexpr int N_THREADS = n_threads(NT);
+  constexpr int RW = ROW_WARPS * NT;                 // row (epilogue) warps; warp RW: producer; RW+1, RW+2: MMA issue / relays
   using C = Cfg<NPASS, NERF, NT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *ring = smem + C::OFF_RING;
@@ -349,14 +354,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     for (int s = 0; s < C::STAGES; ++s) s_last[s] = 0xffffffffu;
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<PAIR>(smem_u32(tmem_slot), C::TMEM_COLS);
+  if (warp == RW + 1) tmem_alloc<PAIR>(smem_u32(tmem_slot), C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   if (PAIR == 2) cluster_sync_all();        // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == RW) {
     // ===== weight producer: this CTA's half of every operand image chunk ======================
     if (lane < PROD_LANES) {
       uint32_t stage = 0, phase = 0, turn = 0;
@@ -381,8 +386,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp >= 9) {
-    const int my_slot = warp - 9;
+  } else if (warp > RW) {
+    const int my_slot = warp - (RW + 1);
     if (leader && my_slot < NT) {
       // ===== MMA issuers (leader CTA): one thread per tile slot, so that neither slot's issue stream
       // waits behind the other's epilogue and the per-step barrier/commit overhead is split in two ====
@@ -491,9 +496,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     }
   } else {
     // ===== row threads: input encoding, per-layer epilogues, heads =============================
-    const int row = (warp & 3) * 32 + lane;            // == TMEM lane; warps w and w+4 share a row
-    const int half = warp >> 2;                        // which half of the columns this thread owns
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int my_t = warp / ROW_WARPS;                 // the tile slot this warp serves (always 0 when NT == 1)
+    const int rwarp = warp % ROW_WARPS;
+    const int row = (rwarp & 3) * 32 + lane;           // == TMEM lane (warp % 4 selects the lane quadrant); warps w and w+4 share a row
+    const int half = rwarp >> 2;                       // which half of the columns this thread owns
+    const int bar_id = 1 + my_t;                       // named barrier of this slot's 256 row threads
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // (ROW_WARPS is a multiple of 4: warp & 3 == rwarp & 3)
     // rows always arrive CTA-locally (per-warp aggregated arrives were measured slower: the __syncwarp lengthens every
     // quarter of the epilogue by more than the serialised arrives cost)
     const uint32_t a_arrive = leader ? bar_a_ready : bar_a_local;
@@ -508,6 +516,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       ANI_TRACE(0);
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
+        if (NT > 1 && t != my_t) continue;
         uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
         gi[t] = ((ut * NT + t) * PAIR + cta_rank) * TILE_M + row;
         valid[t] = gi[t] < n_valid;
@@ -535,6 +544,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         const int n_pad = F.layers[l].n_pad;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
+          if (NT > 1 && t != my_t) continue;
           uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
           float *xchg = s_xchg + t * (TILE_M * 4);           // this slot's exchange between the row's two threads
           const uint32_t t_acc = t_lane + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
@@ -701,7 +711,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               mx = fmaxf(mx, bw[k]);
             }
             scr[half * TILE_M + row] = mx;
-            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(ROW_THREADS) : "memory");
             mx = fmaxf(scr[row], scr[TILE_M + row]);
             float part = 0.f;
 #pragma unroll
@@ -710,7 +720,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               part += bw[k];
             }
             scr[(2 + half) * TILE_M + row] = part;
-            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(ROW_THREADS) : "memory");
             const float inv_sum = 1.0f / (scr[2 * TILE_M + row] + scr[3 * TILE_M + row]);
 #pragma unroll
             for (int k = 0; k < HB; ++k) bw[k] *= inv_sum;
@@ -731,7 +741,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 12; ++j) scr[(4 + j) * TILE_M + row] = M[j];
               }
-              asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+              asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(ROW_THREADS) : "memory");
               if (half == 0 && valid[t]) {
 #pragma unroll
                 for (int j = 0; j < 12; ++j) M[j] += scr[(4 + j) * TILE_M + row];
@@ -746,7 +756,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                 args.tpts_out[3 * gi[t] + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
               }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // the scratch is the next tile's PE operand
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(ROW_THREADS) : "memory");   // the scratch is the next tile's PE operand
           } else {
             // ---- NeRF head: view layer (ReLU) -> rgb_fc in fp32; alpha from the layer-7 epilogue ---
             float rgb[3] = {0.f, 0.f, 0.f};
@@ -770,7 +780,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               xchg[row * 4 + 2] = rgb[1];
               xchg[row * 4 + 3] = rgb[2];
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // the row's two threads meet
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(ROW_THREADS) : "memory");   // the row's two threads meet
             if (half == 0) {
               my_sigma += xchg[row * 4] + s_head[256];
               rgb[0] += xchg[row * 4 + 1] + s_head[257 + 384];
@@ -796,7 +806,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                 }
               }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // s_xchg is rewritten by the next slot / tile
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(ROW_THREADS) : "memory");   // s_xchg is rewritten by the next slot / tile
           }
         }
         acc_phase ^= 1;
@@ -809,7 +819,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (PAIR == 2) cluster_sync_all();        // the leader's MMAs read the peer's shared memory: leave together
-  if (warp == 9) {
+  if (warp == RW + 1) {
     tc_fence_after();
     tmem_dealloc<PAIR>(tmem_base, C::TMEM_COLS);
   }
@@ -997,7 +1007,7 @@ static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
   if (units <= 0) return ANINERF_OK;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(units * kPair));
-  cfg.blockDim = dim3(N_THREADS);
+  cfg.blockDim = dim3(n_threads(NT));
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
