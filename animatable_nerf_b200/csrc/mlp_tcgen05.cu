@@ -15,9 +15,11 @@
 // epilogue is the field's head (softmax + inverse LBS, or alpha/rgb activation + tbounds masking +
 // scatter).
 //
-// NT = 2 (single-pass precision): each CTA holds TWO tile slots and ping-pongs them -- while the
-// tensor core runs layer l of slot 1 the epilogue warps drain layer l of slot 0 -- so MMA and epilogue
-// overlap.  NT = 1 for the split-precision mode (its A operand, hi+lo, fills shared memory).
+// NT = 2 (single-pass precision): each CTA holds TWO tile slots, each with its own eight epilogue warps, and
+// ping-pongs them -- while the tensor core runs layer l of slot 1 the warps of slot 0 drain its layer l -- so
+// MMA and epilogue overlap.  NT = 1 for the split-precision mode (its A operand, hi+lo, fills shared memory):
+// there the accumulator is double-buffered, the epilogue publishes the next A operand in quarters and every
+// 256-wide layer runs as two N = 128 halves, so the tensor pipe never waits for an epilogue (see QP below).
 //
 // Precision modes: NPASS=1 single bf16 product; NPASS=3 "bf16x3": x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // with fp32 accumulation (fp32-equivalent; the blend-weight field needs it for the 1e-5 gate).
@@ -186,36 +188,11 @@ __device__ __forceinline__ void write_pe(uint8_t *a_hi, uint8_t *a_lo, int chunk
   }
 }
 
-// Trilinear corner set for the SMPL-weight gather of the blend-weight head: same geometry as trilinear_corners()
-// (align_corners, border clamp) with the normalisation folded into one multiply by (dim-1)/ext -- the weights feed a
-// 1e-5-gated quantity, not a bit-exact mask, and the exact form's three IEEE divisions and rounding-order chain cost
-// ~3k cycles of dependent latency per row on the two-warps-per-scheduler epilogue threads.
-// gs: lo[3], scale[3] in shared memory.  off[k] is always a valid voxel (out-of-range corners have weight exactly 0).
-__device__ __forceinline__ void fast_corners(const float *gs, const int32_t dim[3], float px, float py, float pz, float w[8], int off[8]) {
-  const float p[3] = {px, py, pz};
-  float fl[3], fr[3];
-  int i0[3], i1[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float lim = (float)(dim[a] - 1);
-    float u = (p[a] - gs[a]) * gs[3 + a];
-    u = fminf(lim, fmaxf(u, 0.0f));
-    const float f = floorf(u);
-    i0[a] = (int)f;
-    i1[a] = min(i0[a] + 1, dim[a] - 1);
-    fr[a] = u - f;
-    fl[a] = 1.0f - fr[a];
-  }
-  const int Y = dim[1], Z = dim[2];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ex = k & 1, sy = (k >> 1) & 1, bz = (k >> 2) & 1;
-    w[k] = ((ex ? fr[2] : fl[2]) * (sy ? fr[1] : fl[1])) * (bz ? fr[0] : fl[0]);
-    off[k] = ((bz ? i1[0] : i0[0]) * Y + (sy ? i1[1] : i0[1])) * Z + (ex ? i1[2] : i0[2]);
-  }
-}
-
-// corner k (ATen order: k&1 east, k>>1&1 south, k>>2 bottom) of fast_corners(): its weight and voxel index
+// One trilinear corner for the SMPL-weight gather of the blend-weight head: same geometry as trilinear_corners() (align_corners,
+// border clamp) with the normalisation folded into one multiply by (dim-1)/ext -- the weights feed a 1e-5-gated quantity, not a
+// bit-exact mask, and the exact form's three IEEE divisions and rounding-order chain cost ~3k cycles of dependent latency per
+// row on the two-warps-per-scheduler epilogue threads.  gs: lo[3], scale[3] in shared memory.  The voxel index is always valid
+// (an out-of-range corner has weight exactly 0).  Corner k in ATen order: k&1 east, k>>1&1 south, k>>2 bottom.
 __device__ __forceinline__ void fast_corner(const float *gs, const int32_t dim[3], float px, float py, float pz, int k, float &w, int &off) {
   const float p[3] = {px, py, pz};
   const int up[3] = {(k >> 2) & 1, (k >> 1) & 1, k & 1};   // axis 0 (X) <-> bottom, 1 (Y) <-> south, 2 (Z) <-> east
