@@ -279,6 +279,11 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
   // epilogue.  The A operand is updated IN PLACE, so the epilogue of half A may only overwrite quarters 0,1 once half B's MMAs
   // have read them: half B commits `bread` (bar_acc + 16) after its K steps over those quarters.
   constexpr bool QP = NT == 1;
+  // XT (blend-weight field, QP): cross-tile prefetch.  The next tile's input encoding is written into the PE chunks during the
+  // idle window of the LAST layer (the PE chunks are dead since layer 5), so the MMA issuer rolls from layer 8 straight into the
+  // next tile's layer 0 while the epilogue warps are still busy with this tile's head; the accumulator buffer alternates with
+  // (layer + tile) so that layer 0 never lands on the buffer the head is reading.
+  constexpr bool XT = QP && !NERF;
   // last weight-stream position consumed from each ring stage: with one MMA thread per slot a thread only waits
   // on the `full` phases of its OWN steps, and a parity wait is only sound once the previous phase is known complete
   volatile uint32_t *s_last = reinterpret_cast<volatile uint32_t *>(smem + C::OFF_BAR + 216);
@@ -372,7 +377,8 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
       const uint32_t a_lbo = (uint32_t)CHUNK_BYTES, a_sbo = 128u;   // K-direction / 8-row-group strides
       const int t = my_slot;
       const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI + t * A_BYTES), a_lo = smem_u32(smem + C::OFF_A_LO + t * A_BYTES);
-      for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+      uint32_t tile_it = 0;
+      for (int64_t ut = unit; ut < n_utiles; ut += n_units, ++tile_it) {
         const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && lane == 0;
         for (int l = 0; l < F.n_layers; ++l) {
           const int n_pad = F.layers[l].n_pad;
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
           const uint32_t b_k_stride = (uint32_t)(n_sub / PAIR) * 16u;   // bytes between K core matrices (this CTA's rows)
           const uint32_t b_lbo = b_k_stride, b_sbo = 128u;
           g += (uint32_t)(t * n_layer_steps);                           // the earlier slots' copies of this layer
-          uint32_t acc = tmem_base + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
+          uint32_t acc = tmem_base + (uint32_t)(QP ? ((l + (XT ? tile_it : 0u)) & 1u) * 256 : t * 256);
           int sub = 0;
           ANI_TRACE(8 + 16 * l + 8 * t + 4);
           // the A operand is ready (QP: its first quarter) and the accumulator has been drained
@@ -483,7 +489,12 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
     // quarter of the epilogue by more than the serialised arrives cost)
     const uint32_t a_arrive = leader ? bar_a_ready : bar_a_local;
     uint32_t acc_phase = 0, acc_b_phase = 0;
-    for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+    uint32_t tile_it = 0;
+    bool pe_ready = false;                       // XT: this tile's encoding was written during the previous tile's last layer
+    int64_t ngi = 0;
+    bool nvalid = false;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    for (int64_t ut = unit; ut < n_utiles; ut += n_units, ++tile_it) {
       const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
       if (args.trace && blockIdx.x == 0 && threadIdx.x == 0 && ut / n_units < 90) args.trace[160 + ut / n_units] = (unsigned long long)clock64();
       int64_t gi[NT];
@@ -495,10 +506,18 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
       for (int t = 0; t < NT; ++t) {
         if (NT > 1 && t != my_t) continue;
         uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
+        sigma[t] = 0.f;
+        if (XT && pe_ready) {                          // encoded (and published) during the previous tile's last layer
+          gi[t] = ngi;
+          valid[t] = nvalid;
+          px[t] = nx;
+          py[t] = ny;
+          pz[t] = nz;
+          continue;
+        }
         gi[t] = ((ut * NT + t) * PAIR + cta_rank) * TILE_M + row;
         valid[t] = gi[t] < n_valid;
         px[t] = py[t] = pz[t] = 0.f;
-        sigma[t] = 0.f;
         if (valid[t]) {
           px[t] = __ldg(args.pts + 3 * gi[t]);
           py[t] = __ldg(args.pts + 3 * gi[t] + 1);
@@ -524,7 +543,7 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
           if (NT > 1 && t != my_t) continue;
           uint8_t *a_hi = smem + C::OFF_A_HI + t * A_BYTES, *a_lo = smem + C::OFF_A_LO + t * A_BYTES;
           float *xchg = s_xchg + t * (TILE_M * 4);           // this slot's exchange between the row's two threads
-          const uint32_t t_acc = t_lane + (uint32_t)(QP ? (l & 1) * 256 : t * 256);
+          const uint32_t t_acc = t_lane + (uint32_t)(QP ? ((l + (XT ? tile_it : 0u)) & 1u) * 256 : t * 256);
           if (!NERF && l < 8) {
             // Initial SMPL weights of this row (this thread: bones 12*half .. +11): ONE trilinear corner per layer, fetched in
             // the idle window before the layer's accumulator is ready and accumulated in registers (ATen's corner order).
@@ -570,6 +589,26 @@ __global__ void __launch_bounds__(n_threads(NT), 1) mlp_kernel(const __grid_cons
           ANI_TRACE(8 + 16 * l + 8 * t);
           mbar_wait(bar_acc + 8 * (QP ? 0 : t), acc_phase, 5 + 10 * t + 100 * l);
           tc_fence_after();
+          if (XT && last) {
+            // The next tile's input encoding.  It must come AFTER this layer's accumulator barrier: an mbarrier arrival is not tagged
+            // with a phase, and only the completed MMAs of layer 8 prove that every thread's layer-8 arrivals on a_ready[] are in.
+            pe_ready = ut + n_units < n_utiles;
+            if (pe_ready) {
+              ngi = (((ut + n_units) * NT + t) * PAIR + cta_rank) * TILE_M + row;
+              nvalid = ngi < n_valid;
+              nx = ny = nz = 0.f;
+              if (nvalid) {
+                nx = __ldg(args.pts + 3 * ngi);
+                ny = __ldg(args.pts + 3 * ngi + 1);
+                nz = __ldg(args.pts + 3 * ngi + 2);
+              }
+              if (half == 0) write_pe<NPASS, 10, 0, 4>(a_hi, a_lo, PE_CHUNK0, row, nx, ny, nz);
+              else write_pe<NPASS, 10, 4, 8>(a_hi, a_lo, PE_CHUNK0, row, nx, ny, nz);
+              fence_proxy_async();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mbar_arrive(a_arrive + 8 * q);
+            }
+          }
           ANI_TRACE(8 + 16 * l + 8 * t + 1);
           if (!last) {
             if (NERF && l == VIEW_LAYER_WRITE) {
