@@ -81,7 +81,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', os.environ.get('ANINERF_SMI_MS', '200'),
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -100,7 +100,7 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         inside = [r for t, r in self.rows if any(a <= t <= b for a, b in self.windows)]
         if not inside:             # region shorter than the sampling period: take the samples around it
-            inside = [r for t, r in self.rows if any(a - 0.1 <= t <= b + 0.1 for a, b in self.windows)] or [r for _, r in self.rows]
+            inside = [r for t, r in self.rows if any(a - 0.3 <= t <= b + 0.3 for a, b in self.windows)] or [r for _, r in self.rows]
         for r in inside:
             try:
                 sm.append(float(r[0]))
