@@ -191,6 +191,26 @@ def test_blend_weight_field_1e5(dev, case):
     assert (gtp.cpu() - tp).abs().max() <= BW_TOL
 
 
+def test_blend_weight_field_single_pass_option(dev, case):
+    """cfg.b200_bw_precision = 1 (one bf16 pass, the two-slot kernel instantiation): ~1e-4, outside the 1e-5 gate -- an opt-in for
+    previews -- but the head (two threads per row, volume gather, fused inverse LBS) must be the same arithmetic."""
+    from animatable_nerf_b200 import synthetic
+    _, _, batch, _ = case
+    sd = synthetic.make_state_dict(seed=0)
+    _, pp = _pose_points(batch, 12000 + 5)
+    init = O.sample_blend_weights(pp, batch['pbw'], batch['pbounds'])[:, :24]
+    idx = batch['latent_index'] + 1
+    bw = O.neural_blend_weights(sd, pp, init, idx)
+    tp = O.inverse_lbs(pp, bw, batch['A'])
+    net = _net(dev, sd, b200_bw_precision=1)
+    gbw = net.calculate_neural_blend_weights(pp.to(dev), init.to(dev), idx.to(dev))
+    assert (gbw.cpu() - bw).abs().max() <= 1e-3
+    gtp, gpbw = net.pose_points_to_tpose_points(pp.to(dev), to_device(batch, dev))
+    assert (gpbw.cpu() - bw).abs().max() <= 1e-3
+    assert (gtp.cpu() - tp).abs().max() <= 1e-3
+    assert float((gbw.sum(dim=1) - 1).abs().max()) <= 1e-5        # still a softmax
+
+
 def test_blend_weight_field_sharper_weights(dev, case):
     """'trained-like' sharper field (all layer weights x1.6): bf16x3 must still hold 1e-5."""
     from animatable_nerf_b200 import synthetic
