@@ -16,7 +16,7 @@ import torch.nn as nn
 from . import _lib, config
 from . import train_ops as T
 from .train_ops import Op
-from .tpose_trainer import _Grads, _Trunk, _w2
+from .tpose_trainer import _Grads, _PlannedTrunk, _w2
 
 N_POINTS = 1024 * 64      # get_sampling_points, :131
 
@@ -32,6 +32,25 @@ class AnimationStep:
     def __init__(self, net, cfg=None):
         self.net = net
         self.cfg = cfg if cfg is not None else getattr(net, 'cfg', None) or config.global_cfg()
+        self._plan = None
+
+    def _ensure_plan(self, m0, m1, dev, sd):
+        """Flat gradient buffer + the six trunk evaluations of a step as planned trunks (static buffers, prebuilt descriptors):
+        observation->canonical: novel field, frozen canonical field (data gradients only), frozen density trunk;
+        canonical->observation: frozen canonical field, frozen density trunk, novel field."""
+        key = (m0, m1, str(dev), tuple(p.data_ptr() for p in sd.values()))
+        if self._plan is None or self._plan['key'] != key:
+            G = _Grads(self.net)
+            d_pe = torch.zeros(m0, 64, device=dev)
+            nv, bw, nf = 'novel_pose_bw.bw_linears', 'bw_linears', 'tpose_human.pts_linears'
+            p0 = _PlannedTrunk(sd, nv, 128, G, m0, dev)
+            c0 = _PlannedTrunk(sd, bw, 128, G, m0, dev, d_pe=d_pe)
+            n0 = _PlannedTrunk(sd, nf, 0, G, m0, dev, pe=c0.pe)
+            c1 = _PlannedTrunk(sd, bw, 128, G, m1, dev)
+            n1 = _PlannedTrunk(sd, nf, 0, G, m1, dev, pe=c1.pe)
+            q1 = _PlannedTrunk(sd, nv, 128, G, m1, dev)
+            self._plan = {'key': key, 'G': G, 'd_pe': d_pe, 'p0': p0, 'c0': c0, 'n0': n0, 'c1': c1, 'n1': n1, 'q1': q1}
+        return self._plan
 
     @torch.no_grad()
     def run(self, batch, wpts, tpts):
@@ -44,7 +63,9 @@ class AnimationStep:
         dev = wpts.device
         T.begin_step(dev)
         wpts, tpts = _lib.f32c(wpts.reshape(-1, 3)), _lib.f32c(tpts.reshape(-1, 3))
-        G = _Grads(net)
+        plan = self._ensure_plan(wpts.shape[0], tpts.shape[0], dev, sd)
+        G = plan['G']
+        G.flat.zero_()
         A = _lib.f32c(batch['A'].reshape(24, 4, 4))
         pvol, tvol = _lib.f32c(batch['pbw'][0]), _lib.f32c(batch['tbw'][0])
         pb, tb = _lib.f32c(batch['pbounds'].reshape(2, 3)), _lib.f32c(batch['tbounds'].reshape(2, 3))
@@ -62,29 +83,27 @@ class AnimationStep:
         def e(*shape):
             return torch.empty(*shape, device=dev)
 
-        def novel_field(pts, vol, bounds):
-            """novel_pose_bw(pts, init, idx): returns (trunk, h8, init25, bw)"""
+        def novel_field(trunk, pts, vol, bounds):
+            """novel_pose_bw(pts, init, idx) on a planned trunk: returns (h8, init25, bw)"""
             m = pts.shape[0]
             init = T.sample_volume(pts, vol, bounds, e(m, 25))
-            trunk = _Trunk(sd, 'novel_pose_bw.bw_linears', 128, G)
-            h8 = trunk.forward(T.pe_forward(pts, 10, e(m, 64)), lat_np)
+            T.pe_forward(pts, 10, trunk.pe[:m])
+            h8 = trunk.forward(m, lat_np)
             delta = T.gemm([(Op(h8), Op(Wfc_np))], e(m, 24), bias=bfc_np)
-            return trunk, h8, init, T.bw_softmax_forward(init, delta, e(m, 24))
+            return h8, init, T.bw_softmax_forward(init, delta, e(m, 24))
 
-        def canonical_field(pts):
+        def canonical_field(trunk, pts):
             """net.calculate_neural_blend_weights(pts, init_tbw, 0) with the frozen stage-1 weights"""
             m = pts.shape[0]
             init = T.sample_volume(pts, tvol, tb, e(m, 25))
-            trunk = _Trunk(sd, 'bw_linears', 128, G)
-            h8 = trunk.forward(T.pe_forward(pts, 10, e(m, 64)), lat0)
+            T.pe_forward(pts, 10, trunk.pe[:m])
+            h8 = trunk.forward(m, lat0)
             delta = T.gemm([(Op(h8), Op(Wfc))], e(m, 24), bias=bfc)
-            return trunk, h8, init, T.bw_softmax_forward(init, delta, e(m, 24))
+            return h8, init, T.bw_softmax_forward(init, delta, e(m, 24))
 
-        def density(pts):
-            """net.tpose_human.calculate_alpha(pts) (frozen)"""
-            m = pts.shape[0]
-            trunk = _Trunk(sd, 'tpose_human.pts_linears', 0, G)
-            h8 = trunk.forward(T.pe_forward(pts, 10, e(m, 64)), None)
+        def density(trunk, m):
+            """net.tpose_human.calculate_alpha(pts) (frozen); the trunk shares the PE buffer of the canonical field"""
+            h8 = trunk.forward(m, None)
             return T.gemm([(Op(h8), Op(Wa))], e(m, 1), bias=ba)
 
         def select(sigma_masked):
@@ -101,28 +120,30 @@ class AnimationStep:
             T.bw_softmax_backward(init, bw, d_bw, d_delta, None)
             T.gemm([(Op(d_delta).T, Op(h8).T)], gWfc_np, accumulate=True, split_k=T.split_for(m))
             T.colsum(d_delta, gbfc_np, accumulate=True)
-            dz = T.gemm([(Op(d_delta), Op(Wfc_np).T)], e(m, 256), relu_mask=h8)
-            trunk.backward(dz, g_lat_np, None)
+            T.gemm([(Op(d_delta), Op(Wfc_np).T)], trunk.dz[0][:m], relu_mask=h8)
+            trunk.backward(m, g_lat_np, False)
 
         losses = torch.zeros(2, device=dev)
         # ---- observation -> canonical (ppts_to_tpose) ---------------------------------------------------------------------
         m0 = wpts.shape[0]
         ppts = T.world_to_pose(wpts, Rm, Th, e(m0, 3))
-        trunk_p, h8p, init_p, pbw = novel_field(ppts, pvol, pb)
+        trunk_p, trunk_c = plan['p0'], plan['c0']
+        h8p, init_p, pbw = novel_field(trunk_p, ppts, pvol, pb)
         tpose = T.inverse_lbs(ppts, pbw, A, e(m0, 3))
-        trunk_c, h8c, init_t, tbw = canonical_field(tpose)
-        sigma = density(tpose)
+        h8c, init_t, tbw = canonical_field(trunk_c, tpose)
+        sigma = density(plan['n0'], m0)
         sm = T.mask_sigma(sigma, tpose, tb, init_p[:, 24:], 25, norm_th, e(m0))
         sel0, n_sel0 = select(sm)
         d_pbw, d_tbw = e(m0, 24), e(m0, 24)
         T.bw_loss(pbw, tbw, sel0, n_sel0, losses[0:1], d_pbw, d_tbw)
         # ---- canonical -> observation (tpose_to_ppts) ---------------------------------------------------------------------
         m1 = tpts.shape[0]
-        _, _, _, tbw_c = canonical_field(tpts)
-        sigma1 = density(tpts).view(-1)
+        _, _, tbw_c = canonical_field(plan['c1'], tpts)
+        sigma1 = density(plan['n1'], m1).view(-1)
         sel1, n_sel1 = select(sigma1)
         pose_pts = T.forward_lbs(tpts, tbw_c, A, e(m1, 3))
-        trunk_q, h8q, init_q, pbw_c = novel_field(pose_pts, pvol, pb)
+        trunk_q = plan['q1']
+        h8q, init_q, pbw_c = novel_field(trunk_q, pose_pts, pvol, pb)
         d_pbw_c, d_unused = e(m1, 24), e(m1, 24)
         T.bw_loss(pbw_c, tbw_c, sel1, n_sel1, losses[1:2], d_pbw_c, d_unused)
 
@@ -131,9 +152,9 @@ class AnimationStep:
         # frozen canonical field: data gradients only, down to the canonical point
         d_delta, d_init = e(m0, 24), e(m0, 24)
         T.bw_softmax_backward(init_t, tbw, d_tbw, d_delta, d_init)
-        dz = T.gemm([(Op(d_delta), Op(Wfc).T)], e(m0, 256), relu_mask=h8c)
-        d_pe = torch.zeros(m0, 64, device=dev)
-        trunk_c.backward(dz, None, d_pe, wgrad=False)
+        T.gemm([(Op(d_delta), Op(Wfc).T)], trunk_c.dz[0][:m0], relu_mask=h8c)
+        d_pe = plan['d_pe'][:m0]
+        trunk_c.backward(m0, None, True, wgrad=False)
         d_tp = T.pe_backward(tpose, d_pe, 10, e(m0, 3), False)
         T.sample_volume_backward(tpose, tvol, tb, d_init, d_tp, True)
         T.inverse_lbs_backward(pbw, A, tpose, d_tp, d_pbw, True)

@@ -50,83 +50,15 @@ class _Grads:
         return v.view(v.shape[0], v.shape[1]) if v.dim() == 3 else v
 
 
-class _Trunk:
-    """8 x (1x1 conv + ReLU) with the skip concat after layer 4 (tpose_nerf_network.py:68-72, 256-260): forward keeping every
-    activation, backward producing weight / bias / latent gradients and (optionally) the gradient of the PE input."""
-
-    def __init__(self, sd, prefix, lat_cols, grads: _Grads):
-        self.W = [_w2(sd[f'{prefix}.{i}.weight']) for i in range(8)]
-        self.b = [sd[f'{prefix}.{i}.bias'].detach() for i in range(8)]
-        self.gW = [grads.w(f'{prefix}.{i}.weight') for i in range(8)]
-        self.gb = [grads.views[f'{prefix}.{i}.bias'] for i in range(8)]
-        self.lat = lat_cols          # number of latent input channels after the 63 PE channels (128 or 0)
-        self.hid0 = 63 + lat_cols    # first hidden column of the skip layer's weight
-
-    def forward(self, pe, lat):
-        """pe (n,>=63) fp32 [PE in the first 63 columns]; lat (1,128) or None -> list H, H[l] = input of layer l, H[8] = output"""
-        n, dev = pe.shape[0], pe.device
-        H = [None] * 9
-        self.beff = [None] * 8
-        for l in range(8):
-            bias = self.b[l]
-            if self.lat and l in (0, 5):
-                bias = torch.empty(1, 256, device=dev)          # latent code folded into the bias: b + W[:, 63:191] @ latent
-                T.gemm([(Op(lat), Op(self.W[l][:, 63:63 + self.lat]))], bias, bias=self.b[l])
-                self.beff[l] = bias
-            if l == 0:
-                segs = [(Op(pe[:, :63]), Op(self.W[0][:, :63]))]
-            elif l == 5:
-                segs = [(Op(pe[:, :63]), Op(self.W[5][:, :63])), (Op(H[5]), Op(self.W[5][:, self.hid0:]))]
-            else:
-                segs = [(Op(H[l]), Op(self.W[l]))]
-            H[l + 1] = T.gemm(segs, torch.empty(n, 256, device=dev), bias=bias, relu=True)
-        self.pe, self.H, self.latv = pe, H, lat
-        return H[8]
-
-    def backward(self, dZ, g_lat, d_pe, wgrad=True):
-        """dZ (n,256): gradient of layer 7's pre-activation.  g_lat (1,128) gradient row of the latent code (accumulated) or None.
-        d_pe (n,>=63) or None: receives the gradient of the PE input (written, not accumulated).
-        wgrad=False: a frozen field (stage-2 training) -- only the data gradients are propagated."""
-        n, dev = dZ.shape[0], dZ.device
-        H, pe = self.H, self.pe
-        sk = T.split_for(n)
-        for l in range(7, -1, -1):
-            W, gW = self.W[l], self.gW[l]
-            # weight gradients  dW[seg] += dZ^T @ X_seg
-            if not wgrad:
-                pass
-            elif l == 0:
-                T.gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, split_k=sk)
-            elif l == 5:
-                T.gemm([(Op(dZ).T, Op(pe[:, :63]).T)], gW[:, :63], accumulate=True, split_k=sk)
-                T.gemm([(Op(dZ).T, Op(H[5]).T)], gW[:, self.hid0:], accumulate=True, split_k=sk)
-            else:
-                T.gemm([(Op(dZ).T, Op(H[l]).T)], gW, accumulate=True, split_k=sk)
-            # bias (and folded latent) gradients
-            if not wgrad:
-                pass
-            elif self.lat and l in (0, 5):
-                db = T.colsum(dZ, torch.empty(1, 256, device=dev))
-                self.gb[l].add_(db.view(-1))
-                Wl = W[:, 63:63 + self.lat]
-                T.gemm([(Op(db).T, Op(self.latv).T)], gW[:, 63:63 + self.lat], accumulate=True)        # d W_lat += db (x) latent
-                T.gemm([(Op(db), Op(Wl).T)], g_lat, accumulate=True)                                  # d latent += db @ W_lat
-            else:
-                T.colsum(dZ, self.gb[l], accumulate=True)
-            # data gradients
-            if d_pe is not None and l in (0, 5):
-                T.gemm([(Op(dZ), Op(W[:, :63]).T)], d_pe[:, :63], accumulate=(l == 0))
-            if l > 0:
-                Wh = W[:, self.hid0:] if l == 5 else W
-                dZ = T.gemm([(Op(dZ), Op(Wh).T)], torch.empty(n, 256, device=dev), relu_mask=H[l])
-        return d_pe
-
-
 class _PlannedTrunk:
-    """`_Trunk` with everything static: activations live in buffers sized for `m_max` rows, and every product of the forward /
-    backward pass is a prebuilt `aninerf_gemm` descriptor -- per call only the row count (M, or K and the split factor of a
-    weight gradient) is patched and the library entry invoked.  ~35 launches per pass cost ~3 us of host time each instead of
-    ~16 us (descriptor construction, operand views, allocations), which is what bounds a 1024-ray training iteration."""
+    """8 x (1x1 conv + ReLU) with the skip concat after layer 4 (tpose_nerf_network.py:68-72, 256-260): forward keeping every
+    activation, backward producing weight / bias / latent gradients and (optionally) the gradient of the PE input.
+    Everything is static: activations live in buffers sized for `m_max` rows, and every product of the forward / backward pass
+    is a prebuilt `aninerf_gemm` descriptor -- per call only the row count (M, or K and the split factor of a weight gradient) is
+    patched and the library entry invoked.  ~35 launches per pass cost ~3 us of host time each instead of ~16 us (descriptor
+    construction, operand views, allocations), which is what bounds a 1024-ray training iteration.  The latent code of the field
+    (lat_cols = 128) is folded into the bias of layers 0 and 5 through an M = 1 product, so its gradient comes out of the same
+    kernel."""
 
     def __init__(self, sd, prefix, lat_cols, grads, m_max, dev, pe=None, d_pe=None):
         self.W = [_w2(sd[f'{prefix}.{i}.weight']) for i in range(8)]
