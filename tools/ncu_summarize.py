@@ -48,10 +48,23 @@ if os.path.exists(src):
     print('wrote launch summary,', len(agg), 'kernels')
 
 # ---- full capture --------------------------------------------------------------------------------
-rep = os.path.join(ROOT, 'gpurun_out', f'prof_{tag}.ncu-rep')
-if os.path.exists(rep):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+# (several captures of the same command may be merged: extra tags after the round number, e.g. `r2f 01 r2g`; the first
+# occurrence of a kernel wins)
+reps = [os.path.join(ROOT, 'gpurun_out', f'prof_{t}.ncu-rep') for t in [tag] + sys.argv[3:]]
+reps = [r for r in reps if os.path.exists(r)]
+if reps:
+    rows, seen, row_units = None, set(), {}
+    for rep in reps:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        part = list(csv.reader(io.StringIO(raw)))
+        if rows is None:
+            rows = part[:2]
+        ci = part[0].index('Kernel Name')
+        for r in part[2:]:
+            if r[ci] not in seen and part[0] == rows[0]:
+                seen.add(r[ci])
+                rows.append(r)
+                row_units[id(r)] = part[1]          # ncu scales the units per report
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     want = [
@@ -75,13 +88,13 @@ if os.path.exists(rep):
     with open(os.path.join(out, f'r{rnd}_ncu_full_summary.md'), 'w') as f:
         f.write(f'# Round {int(rnd)} -- `ncu --set full --clock-control none --import-source on` of the hot kernels\n\n'
                 'Command: `python bench.py --steps 3 --warmup 3 --no-cpu` (B200, 1 GPU), kernels `mlp_kernel|composite_kernel|mask_kernel`, '
-                f'launch-skip 24, count 4.\nReport file: gpurun_out/prof_{tag}.ncu-rep (scratch, not committed); numbers below are per launch.\n'
+                f'launch-skip 24, count 4 (+ a second capture of the two MLP kernels only).\nReport files: ' + ', '.join('gpurun_out/' + os.path.basename(r) for r in reps) + ' (scratch, not committed); numbers below are per launch.\n'
                 '`traffic` of bench.py\'s roofline object = DRAM read + DRAM write of the kernel\'s row here.\n')
         for r in rows[2:]:
             f.write(f'\n## `{r[col["Kernel Name"]][:90]}`\n\n| metric | value |\n|---|---|\n')
             for label, key in want:
                 if key in col:
-                    f.write(f'| {label} | {r[col[key]]} {units[col[key]]} |\n')
+                    f.write(f'| {label} | {r[col[key]]} {row_units[id(r)][col[key]]} |\n')
     # per-launch DRAM traffic of each kernel, read by bench.py for roofline.traffic
     import json
 
@@ -93,8 +106,9 @@ if os.path.exists(rep):
         name = r[col['Kernel Name']]
         name = (name[5:] if name.startswith('void ') else name).split('(')[0]
         tensor[name] = float(r[col['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']].replace(',', ''))
-        traffic[name] = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) + \
-            to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
-    json.dump({'source': f'ncu --set full, gpurun_out/prof_{tag}.ncu-rep, bench.py --steps 3 --warmup 3 --no-cpu', 'unit': 'bytes per launch',
+        u = row_units[id(r)]
+        traffic[name] = to_bytes(r[col['dram__bytes_read.sum']], u[col['dram__bytes_read.sum']]) + \
+            to_bytes(r[col['dram__bytes_write.sum']], u[col['dram__bytes_write.sum']])
+    json.dump({'source': 'ncu --set full, ' + ', '.join('gpurun_out/' + os.path.basename(r) for r in reps) + ', bench.py --steps 3 --warmup 3 --no-cpu', 'unit': 'bytes per launch',
                'dram_read_plus_write': traffic, 'tensor_pipe_active_pct': tensor}, open(os.path.join(out, f'r{rnd}_traffic.json'), 'w'), indent=1)
     print('wrote full summary,', len(rows) - 2, 'kernels')
