@@ -226,7 +226,9 @@ typedef struct {
   float *rgb_map;    /* (n_rays,3) */
   float *acc_map;    /* (n_rays,) */
   float *depth_map;  /* (n_rays,) */
-  float *raw;        /* (n_rays*S,4) dense; REQUIRED (also the compositing input) */
+  float *raw;        /* (n_rays*S,4) dense, zero off the active set: required with want_bw (a training-contract output);
+                        NULL in render-only mode: the active rows stay compact in the workspace and are composited
+                        through the mask words -- same maps bit for bit, no 16 B/sample buffer, no memset */
   /* want_bw outputs, each with room for n_rays*S rows (only the first *n_active are written) */
   float *pbw_all;      /* (n_active,24) */
   float *tbw_all;      /* (n_active,24) */
@@ -250,7 +252,7 @@ int aninerf_render_rays(aninerf_net *net, const aninerf_frame *frame_host, const
 /* tpose_renderer_mmsk.Renderer.render (tpose_renderer_mmsk.py:99-166): the same frame render with the
  * samples culled by the training-view silhouettes BEFORE the network (so the per-chunk argmin forcing
  * of Network.forward runs over the survivors only, and a chunk without survivors evaluates nothing).
- * out_host->raw is still required (compositing input); want_bw must be 0 (the reference returns maps only). */
+ * want_bw must be 0 (the reference returns maps only). */
 int aninerf_render_rays_culled(aninerf_net *net, const aninerf_frame *frame_host, const aninerf_render_params *params_host,
                                const aninerf_silhouettes *sil_host, const float *ray_o, const float *ray_d, const float *near,
                                const float *far, const float *t_vals, const float *t_rand, int64_t n_rays,
