@@ -83,6 +83,15 @@ def test_train_iteration_reduces_the_loss(dev):
     w = _wrapper(dev, sd)
     opt = torch.optim.Adam(w.net.parameters(), lr=5e-4)
     b = to_device(tb, dev)
+    # the fast path of train_iteration (flat buffer -> .grad) carries the same gradients as loss.backward() + clip_grad_value_
+    _, loss, _, _ = w(b, t_rand=t_rand)
+    loss.mean().backward()
+    torch.nn.utils.clip_grad_value_(w.net.parameters(), 40)
+    via_autograd = {k: p.grad.clone() for k, p in w.net.named_parameters()}
+    w.net.zero_grad()
+    train_iteration(w, b, torch.optim.SGD(w.net.parameters(), lr=0.0), t_rand=t_rand)
+    for k, p in w.net.named_parameters():
+        assert torch.equal(p.grad, via_autograd[k]), k
     losses = []
     for _ in range(5):
         _, stats = train_iteration(w, b, opt, t_rand=t_rand)
