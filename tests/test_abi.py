@@ -70,3 +70,27 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in animatable_nerf_b200/_lib.py against the C compiler's view of include/aninerf_b200.h: sizes and the
+    offset of every struct's last field (a mismatch would silently shift pointers across the C ABI)."""
+    import ctypes as C
+    import subprocess
+    from animatable_nerf_b200 import _lib
+    pairs = [('aninerf_camera', _lib.Camera, 'W'), ('aninerf_layer', _lib.Layer, 'relu'), ('aninerf_frame', _lib.Frame, 'bw_latent_index_dev'),
+             ('aninerf_render_params', _lib.RenderParams, 'nerf_precision'), ('aninerf_render_outputs', _lib.RenderOutputs, 'chunk_offsets'),
+             ('aninerf_silhouettes', _lib.Silhouettes, 'W'), ('aninerf_peer_gather', _lib.PeerGather, 'rank'),
+             ('aninerf_gemm_seg', _lib.GemmSeg, 'K'), ('aninerf_gemm', _lib.Gemm, 'split_k')]
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "aninerf_b200.h")}"', 'int main(void) {']
+    for cname, _, last in pairs:
+        src.append(f'  printf("%zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));')
+    src += ['  return 0;', '}']
+    c_file, exe = tmp_path / 'layout.c', tmp_path / 'layout'
+    c_file.write_text('\n'.join(src))
+    subprocess.run(['gcc', '-std=c99', '-o', str(exe), str(c_file)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    for i, (cname, ct, last) in enumerate(pairs):
+        size, off = int(out[2 * i]), int(out[2 * i + 1])
+        assert C.sizeof(ct) == size, (cname, C.sizeof(ct), size)
+        assert getattr(ct, last).offset == off, (cname, last)
