@@ -46,6 +46,25 @@ def test_bad_arguments_are_rejected_not_crashed():
     assert rc == -1 and b'invalid argument' in L.aninerf_last_error()
     rc = L.aninerf_sample_points(None, None, None, None, None, None, 4, 64, None, None, None, None)
     assert rc == -1
+    # the training-step, culling and tiled-render entries validate their arguments the same way (no GPU is touched)
+    import ctypes as C
+    g = _lib.Gemm()
+    g.n_seg, g.M, g.N = 1, 8, 8
+    assert L.aninerf_gemm_x3(C.byref(g), None, 0, None) == -1                         # no output / operand pointers
+    assert L.aninerf_colsum(None, 8, 8, 8, None, 0, None, 0, None) == -1
+    assert L.aninerf_pe_forward(None, 8, 10, None, 64, None) == -1
+    assert L.aninerf_bw_softmax_forward(None, 25, None, 8, None, None) == -1
+    assert L.aninerf_inverse_lbs_backward(None, None, None, None, 8, None, 0, None) == -1
+    assert L.aninerf_composite_backward(None, None, 8, 64, 0, None, None) == -1
+    assert L.aninerf_img_loss(None, None, None, 8, None, None, None) == -1
+    assert L.aninerf_inside_all_views(None, 8, None, None, None) == -1
+    fr, pr, ro = _lib.Frame(), _lib.RenderParams(n_samples=64, chunk_rays=2048), _lib.RenderOutputs()
+    pg = _lib.PeerGather()
+    pg.world, pg.rank = 9, 0                                                            # more peers than one NVSwitch box has
+    assert L.aninerf_render_rays_tiled(None, C.byref(fr), C.byref(pr), None, C.byref(pg), None, None, None, None, None, None, 4,
+                                       C.byref(ro), None, 0, None) == -1
+    assert L.aninerf_render_rays_culled(None, C.byref(fr), C.byref(pr), None, None, None, None, None, None, None, 4, C.byref(ro), None, 0,
+                                        None) == -1
 
 
 def test_no_cpu_fallback():
