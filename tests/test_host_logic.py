@@ -209,3 +209,19 @@ def test_load_frame_from_sequence_files(tmp_path):
         assert np.allclose(got[k], frame[k], atol=1e-6), k
     assert np.allclose(got['pbounds'], frame['pbounds'], atol=1e-5)
     assert got['Th'].shape == (1, 3) and int(got['latent_index']) == 2
+
+
+def test_peer_scatter_row_formula_matches_the_shard_order():
+    """composite_kernel's fused gather stores local ray r of rank k at frame row ((r // 2048) * world + k) * 2048 + r % 2048
+    (csrc/geometry.cu, PeerScatter): exactly the frame index ray_tiles.shard_indices assigns to that local ray."""
+    from animatable_nerf_b200 import ray_tiles
+    for n_rays, world in ((242907, 8), (5000, 2), (2048 * 3 + 1, 4), (100, 8)):
+        seen = []
+        for rank in range(world):
+            idx = ray_tiles.shard_indices(n_rays, rank, world)
+            r = torch.arange(idx.numel())
+            lc = r // ray_tiles.CHUNK
+            row = (lc * world + rank) * ray_tiles.CHUNK + (r - lc * ray_tiles.CHUNK)
+            assert torch.equal(row, idx), (n_rays, world, rank)
+            seen.append(idx)
+        assert torch.equal(torch.sort(torch.cat(seen))[0], torch.arange(n_rays))
