@@ -120,6 +120,7 @@ PROTOTYPES = {
     'aninerf_composite_backward': (_I32, [_VP, _VP, _I64, _I32, _I32, _VP, _VP]),
     'aninerf_img_loss': (_I32, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     'aninerf_select_rows': (_I32, [_VP, _VP, _I32, _F, _VP, _VP, _VP]),
+    'aninerf_gather_selected_rows': (_I32, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
     'aninerf_bw_loss': (_I32, [_VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     'aninerf_query_workspace_bytes': (_I64, [_I64, _I64]),
     'aninerf_query_alpha': (_I32, [_VP, C.POINTER(Frame), _VP, _I64, _I64, _F, _I32, _I32, _VP, _VP, _VP, _I64, _VP]),

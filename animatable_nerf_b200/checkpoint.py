@@ -12,6 +12,7 @@ files of a processed ZJU-MoCap / H36M sequence.
 from __future__ import annotations
 
 import os
+import shutil
 
 import numpy as np
 import torch
@@ -49,8 +50,13 @@ def save_model(net, optim, scheduler, recorder, model_dir, epoch, last=False):
 
 
 def load_model(net, optim, scheduler, recorder, model_dir, resume=True, epoch=-1):
-    """-> the epoch to continue with (0 when there is nothing to resume)"""
-    if not resume or not os.path.exists(model_dir):
+    """-> the epoch to continue with (0 when there is nothing to resume).  `resume=False` removes `model_dir` first, as the
+    reference does (`os.system('rm -rf ...')`, lib/utils/net_utils.py:295-296): a fresh run must not inherit the previous run's
+    `latest.pth` or have its numbered checkpoints pruned together with the old ones."""
+    if not resume:
+        shutil.rmtree(model_dir, ignore_errors=True)
+        return 0
+    if not os.path.exists(model_dir):
         return 0
     path = _pick(model_dir, epoch)
     if path is None:

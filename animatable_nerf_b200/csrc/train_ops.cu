@@ -398,7 +398,91 @@ __global__ void __launch_bounds__(1024) bw_loss_kernel(const float *__restrict__
   if (threadIdx.x == 0) *loss = total / denom;
 }
 
-// gather the selected rows (ascending order) into the (n_sel, 24) outputs of the training contract
+// ---- the selected rows (ascending order) -> the (n_sel, 24) `pbw` / `tbw` outputs of the contract (tpose_nerf_network.py:195-196) ----
+// per chunk: number of selected rows
+__global__ void __launch_bounds__(256) count_sel_kernel(const uint8_t *__restrict__ sel, const int32_t *__restrict__ chunk_offsets,
+                                                        int32_t *__restrict__ counts) {
+  __shared__ int cnts[8];
+  const int b = chunk_offsets[blockIdx.x], e = chunk_offsets[blockIdx.x + 1];
+  int cnt = 0;
+  for (int i = b + threadIdx.x; i < e; i += blockDim.x) cnt += sel[i] ? 1 : 0;
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) cnts[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int w = 0; w < 8; ++w) c += cnts[w];
+    counts[blockIdx.x] = c;
+  }
+}
+
+// exclusive scan of the per-chunk counts in place (+ the total at [n]); one block, chunks are few (a 1024x1024 frame has ~120)
+__global__ void __launch_bounds__(1024) scan_sel_kernel(int32_t *__restrict__ counts, int n) {
+  __shared__ int part[1024];
+  const int per = (n + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < 1024; ++t) {
+      const int v = part[t];
+      part[t] = run;
+      run += v;
+    }
+    counts[n] = run;
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int i = b; i < e; ++i) {
+    const int v = counts[i];
+    counts[i] = run;
+    run += v;
+  }
+}
+
+// stable gather of the selected 24-float rows of a chunk: positions by ballot + prefix inside 256-row tiles, rows copied as
+// six float4 by all threads (coalesced on both sides)
+__global__ void __launch_bounds__(256) gather_sel_rows_kernel(const uint8_t *__restrict__ sel, const int32_t *__restrict__ chunk_offsets,
+                                                              const int32_t *__restrict__ sel_offsets, const float4 *__restrict__ src_a,
+                                                              const float4 *__restrict__ src_b, float4 *__restrict__ dst_a,
+                                                              float4 *__restrict__ dst_b) {
+  constexpr int Q = ANINERF_N_BONES / 4;             // float4 per row
+  __shared__ int pos[256];
+  __shared__ int warp_cnt[8];
+  const int b = chunk_offsets[blockIdx.x], e = chunk_offsets[blockIdx.x + 1];
+  int base = sel_offsets[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = b; t0 < e; t0 += 256) {
+    const int i = t0 + (int)threadIdx.x;
+    const bool on = i < e && sel[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      before += w < warp ? warp_cnt[w] : 0;
+      total += warp_cnt[w];
+    }
+    pos[threadIdx.x] = on ? before + __popc(bal & ((1u << lane) - 1u)) : -1;
+    __syncthreads();
+    const int rows = min(256, e - t0);
+    for (int j = threadIdx.x; j < rows * Q; j += 256) {
+      const int r = j / Q, q = j - r * Q;
+      const int p = pos[r];
+      if (p >= 0) {
+        const int64_t s = (int64_t)(t0 + r) * Q + q, d = (int64_t)(base + p) * Q + q;
+        dst_a[d] = src_a[s];
+        if (src_b) dst_b[d] = src_b[s];
+      }
+    }
+    base += total;
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(float *__restrict__ p, int64_t n, float v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -518,6 +602,25 @@ int aninerf_select_rows(const float *sigma_masked, const int32_t *chunk_offsets,
   ANI_CUDA(cudaMemsetAsync(n_sel, 0, 4, (cudaStream_t)stream));
   if (n_chunks == 0) return ANINERF_OK;
   select_rows_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(sigma_masked, chunk_offsets, train_th, sel, n_sel);
+  ANI_LAUNCHED();
+  return ANINERF_OK;
+}
+
+int aninerf_gather_selected_rows(const uint8_t *sel, const int32_t *chunk_offsets, int32_t n_chunks, const float *src_a, const float *src_b,
+                                 float *dst_a, float *dst_b, int32_t *sel_offsets, void *stream) {
+  ANI_CHECK_ARG(sel && chunk_offsets && src_a && dst_a && sel_offsets && n_chunks >= 0 && (!src_b || dst_b));
+  ANI_CHECK_ARG((((uintptr_t)src_a | (uintptr_t)src_b | (uintptr_t)dst_a | (uintptr_t)dst_b) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_chunks == 0) {
+    ANI_CUDA(cudaMemsetAsync(sel_offsets, 0, 4, st));
+    return ANINERF_OK;
+  }
+  count_sel_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(sel, chunk_offsets, sel_offsets);
+  ANI_LAUNCHED();
+  scan_sel_kernel<<<1, 1024, 0, st>>>(sel_offsets, n_chunks);
+  ANI_LAUNCHED();
+  gather_sel_rows_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(sel, chunk_offsets, sel_offsets, (const float4 *)src_a, (const float4 *)src_b,
+                                                             (float4 *)dst_a, (float4 *)dst_b);
   ANI_LAUNCHED();
   return ANINERF_OK;
 }

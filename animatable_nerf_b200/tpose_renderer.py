@@ -18,22 +18,6 @@ from . import _lib, config
 from .tpose_nerf_network import _frame_struct
 
 
-def select_forced_argmax(sigma_masked: torch.Tensor, chunk_offsets: torch.Tensor, train_th: float) -> torch.Tensor:
-    """alpha_ind of tpose_nerf_network.py:192-194 for all chunks at once: sigma > train_th, plus the
-    first arg-max row of every chunk.  sigma_masked (n',), chunk_offsets (n_chunks+1,) -> bool (n',)."""
-    n = sigma_masked.numel()
-    sel = sigma_masked > train_th
-    counts = (chunk_offsets[1:] - chunk_offsets[:-1]).long()
-    n_chunks = counts.numel()
-    chunk_id = torch.repeat_interleave(torch.arange(n_chunks, device=sigma_masked.device), counts, output_size=n)
-    cmax = torch.full((n_chunks,), float('-inf'), device=sigma_masked.device).scatter_reduce(0, chunk_id, sigma_masked, 'amax')
-    rows = torch.arange(n, device=sigma_masked.device)
-    cand = torch.where(sigma_masked == cmax[chunk_id], rows, torch.full_like(rows, n))
-    first = torch.full((n_chunks,), n, dtype=rows.dtype, device=rows.device).scatter_reduce(0, chunk_id, cand, 'amin')
-    sel[first[first < n]] = True
-    return sel
-
-
 class Renderer:
     def __init__(self, net, cfg=None):
         self.net = net
@@ -117,24 +101,75 @@ class Renderer:
         out['_keep'] = (keep, o, d, near, far, tr, silhouettes)
         return out
 
+    # ---------------------------------------------------------------------------------------
     @torch.no_grad()
+    def select_rows(self, out):
+        """alpha_ind of tpose_nerf_network.py:192-194 for the whole frame on the device (`aninerf_select_rows`: sigma > train_th
+        plus the first arg-max row of every 2048-ray chunk).  out: a want_bw result of render_device.
+        Returns (sel uint8 (n,), n_sel int32 (1,)) device tensors; only the first n_active entries of sel are meaningful."""
+        dev = out['sigma_masked'].device
+        n_chunks = out['chunk_offsets'].numel() - 1
+        sel = torch.empty(out['sigma_masked'].numel(), dtype=torch.uint8, device=dev)
+        n_sel = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().aninerf_select_rows(_lib.ptr(out['sigma_masked']), _lib.ptr(out['chunk_offsets']), n_chunks,
+                                                  float(config.get(self.cfg, 'train_th')), _lib.ptr(sel), _lib.ptr(n_sel), _lib.stream_ptr(dev)))
+        return sel, n_sel
+
+    @torch.no_grad()
+    def gather_selected(self, out, sel, n_sel_host):
+        """pbw[alpha_ind], tbw[alpha_ind] (tpose_nerf_network.py:195-196) -> two (n_sel, 24) device tensors, rows ascending."""
+        dev = sel.device
+        n_chunks = out['chunk_offsets'].numel() - 1
+        pbw = torch.empty(max(n_sel_host, 1), 24, device=dev)
+        tbw = torch.empty(max(n_sel_host, 1), 24, device=dev)
+        offs = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().aninerf_gather_selected_rows(_lib.ptr(sel), _lib.ptr(out['chunk_offsets']), n_chunks, _lib.ptr(out['pbw_all']),
+                                                           _lib.ptr(out['tbw_all']), _lib.ptr(pbw), _lib.ptr(tbw), _lib.ptr(offs), _lib.stream_ptr(dev)))
+        return pbw[:n_sel_host], tbw[:n_sel_host]
+
+    @staticmethod
+    def _to_host(tensors, device):
+        """One batched device->host transfer into pinned buffers (torch's caching host allocator recycles them), one sync.
+        The reference's per-chunk `.detach().cpu()` (tpose_renderer.py:154-155) goes through pageable memory at a fraction of
+        the PCIe rate; the results are ordinary CPU tensors either way."""
+        host = {}
+        for k, v in tensors.items():
+            h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            h.copy_(v, non_blocking=True)
+            host[k] = h
+        torch.cuda.current_stream(device).synchronize()
+        return host
+
     def render(self, batch):
+        """Renderer.render (tpose_renderer.py:159-186).  No gradient required: CPU tensors (:154-155).  Gradient enabled on a
+        training-mode network: device tensors that carry the autograd graph to the Network parameters (the contract
+        tpose_trainer.NetworkWrapper relies on, lib/train/trainers/tpose_trainer.py:28)."""
+        if torch.is_grad_enabled() and self.net.training and any(p.requires_grad for p in self.net.parameters()):
+            from .tpose_trainer import render_with_grad
+            return render_with_grad(self, batch)
+        with torch.no_grad():
+            return self._render_eval(batch)
+
+    def _render_eval(self, batch):
         cfg = self.cfg
         ray_o = batch['ray_o']
         R = ray_o.shape[1]
+        dev = ray_o.device
         S = int(config.get(cfg, 'N_samples'))
         t_rand = None
         if config.get(cfg, 'perturb') > 0. and self.net.training:
             # the reference draws the jitter on the CPU generator (tpose_renderer.py:35)
-            t_rand = torch.rand(1, R, S).to(ray_o.device)
+            t_rand = torch.rand(1, R, S).to(dev)
         render_only = bool(config.get(cfg, 'b200_render_only'))
         out = self.render_device(batch, t_rand=t_rand, want_bw=not render_only)
         ret = {'rgb_map': out['rgb_map'].view(1, R, 3), 'acc_map': out['acc_map'].view(1, R), 'depth_map': out['depth_map'].view(1, R)}
-        if not render_only:
-            n_active = int(out['n_active'].item())
-            sel = select_forced_argmax(out['sigma_masked'][:n_active], out['chunk_offsets'], float(config.get(cfg, 'train_th')))
-            ret['raw'] = out['raw'].view(1, R * S, 4)
-            ret['pbw'] = out['pbw_all'][:n_active][sel].view(1, -1, 24)
-            ret['tbw'] = out['tbw_all'][:n_active][sel].view(1, -1, 24)
-        # tpose_renderer.py:154-155: outputs go to the host when no gradient is attached (always, this round)
-        return {k: v.detach().cpu() for k, v in ret.items()}
+        if render_only:
+            return self._to_host(ret, dev)
+        sel, n_sel = self.select_rows(out)
+        ret['raw'] = out['raw'].view(1, R * S, 4)
+        ret['_n_sel'] = n_sel
+        host = self._to_host(ret, dev)                       # maps + raw + the selected-row count: one sync
+        k = int(host.pop('_n_sel')[0])
+        pbw, tbw = self.gather_selected(out, sel, k)
+        host.update(self._to_host({'pbw': pbw.view(1, k, 24), 'tbw': tbw.view(1, k, 24)}, dev))
+        return host

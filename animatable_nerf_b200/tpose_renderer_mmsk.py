@@ -58,10 +58,12 @@ class Renderer(tpose_renderer.Renderer):
         return out.bool().view(pts.shape[0], -1)
 
     @torch.no_grad()
-    def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None):
+    def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None, peers=None, keep_raw=False):
+        """Same parameters as tpose_renderer.Renderer.render_device (incl. `peers`: the fused peer-memory image gather of the
+        ray-tiled multi-GPU path); the culled renderer never produces pbw / tbw (tpose_renderer_mmsk.py:135-139)."""
         if silhouettes is None:
             silhouettes = silhouettes_struct(batch)
-        return super().render_device(batch, t_rand=t_rand, want_bw=False, silhouettes=silhouettes)
+        return super().render_device(batch, t_rand=t_rand, want_bw=False, silhouettes=silhouettes, peers=peers, keep_raw=keep_raw)
 
     @torch.no_grad()
     def render(self, batch):
@@ -75,4 +77,4 @@ class Renderer(tpose_renderer.Renderer):
         out = self.render_device(batch, t_rand=t_rand)
         ret = {'rgb_map': out['rgb_map'].view(1, R, 3), 'acc_map': out['acc_map'].view(1, R), 'depth_map': out['depth_map'].view(1, R)}
         # tpose_renderer_mmsk.py:135-139: always detached host tensors
-        return {k: v.detach().cpu() for k, v in ret.items()}
+        return self._to_host(ret, ray_o.device)

@@ -194,18 +194,24 @@ class TrainStep:
         self._renderer = Renderer(net, self.cfg)
         self._ws = None
         self._plan = None
+        self._generation = 0          # bumped by every forward pass: the static activation buffers belong to the newest one
 
-    def _ensure_plan(self, n, dev, sd):
+    def _ensure_plan(self, m, dev, sd):
         """Static state of the step: the flat gradient buffer and the three planned trunks (posed / canonical blend-weight
-        field, NeRF trunk), sized for n = n_rays * N_samples rows; rebuilt when the size, device or parameter storage changes."""
-        key = (n, str(dev), tuple(p.data_ptr() for p in sd.values()))
-        if self._plan is None or self._plan['key'] != key:
-            G = _Grads(self.net)
-            d_pe = torch.zeros(n, 64, device=dev)
-            tp = _PlannedTrunk(sd, 'bw_linears', 128, G, n, dev)
-            tc = _PlannedTrunk(sd, 'bw_linears', 128, G, n, dev, d_pe=d_pe)
-            tn = _PlannedTrunk(sd, 'tpose_human.pts_linears', 0, G, n, dev, pe=tc.pe, d_pe=d_pe)
-            self._plan = {'key': key, 'G': G, 'd_pe': d_pe, 'trunk_p': tp, 'trunk_c': tc, 'trunk_n': tn}
+        field, NeRF trunk), sized for the ACTIVE row count m of the batch (rounded up; it only grows) -- not for the nominal
+        n_rays * N_samples rows, of which a training batch keeps a few per cent.  Rebuilt when the capacity, device or
+        parameter storage changes."""
+        ptrs = tuple(p.data_ptr() for p in sd.values())
+        if self._plan is not None and self._plan['ptrs'] == ptrs and self._plan['dev'] == str(dev) and self._plan['cap'] >= m:
+            return self._plan
+        cap = max(4096, (m + 4095) // 4096 * 4096, self._plan['cap'] if self._plan is not None else 0)
+        self._plan = None                                    # release the old buffers first
+        G = _Grads(self.net)
+        d_pe = torch.zeros(cap, 64, device=dev)
+        tp = _PlannedTrunk(sd, 'bw_linears', 128, G, cap, dev)
+        tc = _PlannedTrunk(sd, 'bw_linears', 128, G, cap, dev, d_pe=d_pe)
+        tn = _PlannedTrunk(sd, 'tpose_human.pts_linears', 0, G, cap, dev, pe=tc.pe, d_pe=d_pe)
+        self._plan = {'ptrs': ptrs, 'dev': str(dev), 'cap': cap, 'G': G, 'd_pe': d_pe, 'trunk_p': tp, 'trunk_c': tc, 'trunk_n': tn}
         return self._plan
 
     def _workspace(self, nbytes, dev):
@@ -217,6 +223,24 @@ class TrainStep:
     def run(self, batch, t_rand=None):
         """Returns (ret, stats, grads): ret = the Renderer.render training contract (device tensors), stats = device scalars
         bw_loss / img_loss / loss, grads = _Grads (d loss / d parameter)."""
+        s = self.forward_pass(batch, t_rand)
+        losses, d_rgb_map, d_pbw, d_tbw = self.loss_gradients(s, batch)
+        G = self.backward_pass(s, d_rgb_map, d_pbw, d_tbw)
+        stats = {'bw_loss': losses[0], 'img_loss': losses[1], 'loss': losses[0] + losses[1]}
+        return self.contract(s), stats, G
+
+    @staticmethod
+    def contract(s):
+        """The Renderer.render training contract (tpose_renderer.py:159-186) of a forward pass, device tensors."""
+        R, n = s['R'], s['n']
+        selb = s['sel'].bool()
+        return {'rgb_map': s['rgb_map'].view(1, R, 3), 'acc_map': s['acc_map'].view(1, R), 'depth_map': s['depth_map'].view(1, R),
+                'raw': s['raw'].view(1, n, 4), 'pbw': s['pbw'][selb].view(1, -1, 24), 'tbw': s['tbw'][selb].view(1, -1, 24)}
+
+    @torch.no_grad()
+    def forward_pass(self, batch, t_rand=None):
+        """Network.forward + raw2outputs of one training batch, keeping every activation the backward pass needs (in the
+        step's static buffers: a later forward pass invalidates this one's state, `backward_pass` checks)."""
         cfg, net, L = self.cfg, self.net, _lib.lib()
         sd = dict(net.named_parameters())
         if 'novel_pose_bw.bw_fc.weight' in sd and config.get(cfg, 'test_novel_pose'):
@@ -254,10 +278,9 @@ class TrainStep:
         m = int(n_active.item())                      # the reference syncs here too (boolean indexing, tpose_nerf_network.py:155-157)
         index, ppts, viewdir, dists = index[:m], ppts_all[:m], vd_all[:m], dists_all[:m]
 
-        plan = self._ensure_plan(n, dev, sd)
-        G = plan['G']
-        G.flat.zero_()
-        trunk_p, trunk_c, trunk_n, d_pe_all = plan['trunk_p'], plan['trunk_c'], plan['trunk_n'], plan['d_pe']
+        plan = self._ensure_plan(m, dev, sd)
+        self._generation += 1
+        trunk_p, trunk_c, trunk_n = plan['trunk_p'], plan['trunk_c'], plan['trunk_n']
         A = _lib.f32c(batch['A'].reshape(24, 4, 4))
         pvol, tvol = _lib.f32c(batch['pbw'][0]), _lib.f32c(batch['tbw'][0])
         pb, tb = _lib.f32c(batch['pbounds'].reshape(2, 3)), _lib.f32c(batch['tbounds'].reshape(2, 3))
@@ -305,6 +328,24 @@ class TrainStep:
         n_sel = torch.zeros(1, dtype=torch.int32, device=dev)
         _lib.check(L.aninerf_select_rows(_lib.ptr(sigma_masked), _lib.ptr(chunk_offsets), n_chunks, float(config.get(cfg, 'train_th')),
                                          _lib.ptr(sel), _lib.ptr(n_sel), st))
+        self._keep = (keep, o, d, near, far, tr, A, pvol, tvol, pb, tb)
+        T.end_step(dev)
+        return dict(gen=self._generation, R=R, S=S, n=n, m=m, dev=dev, white=pr.white_bkgd, latent_index=latent_index, sd=sd, plan=plan,
+                    index=index, ppts=ppts, viewdir=viewdir, dists=dists, z_vals=z_vals, chunk_offsets=chunk_offsets, A=A, pvol=pvol, tvol=tvol,
+                    pb=pb, tb=tb, lat_n=lat_n, h8p=h8p, h8c=h8c, h8n=h8n, init_p=init_p, init_t=init_t, pbw=pbw, tbw=tbw, tpts=tpts,
+                    feat=feat, f2=f2, pe_v=pe_v, hv=hv, raw=raw, sigma_masked=sigma_masked, rgb_map=rgb_map, acc_map=acc_map,
+                    depth_map=depth_map, sel=sel, n_sel=n_sel)
+
+    @torch.no_grad()
+    def loss_gradients(self, s, batch):
+        """The two losses of tpose_trainer.py:48-63 and their gradients w.r.t. rgb_map (R,3), pbw and tbw (m,24; zero on the
+        rows `alpha_ind` drops).  Returns (losses (2,) = [bw_loss, img_loss], d_rgb_map, d_pbw, d_tbw)."""
+        L, dev, m, R = _lib.lib(), s['dev'], s['m'], s['R']
+        st = _lib.stream_ptr(dev)
+        pbw, tbw, sel, n_sel, rgb_map = s['pbw'], s['tbw'], s['sel'], s['n_sel'], s['rgb_map']
+
+        def e(*shape):
+            return torch.empty(*shape, device=dev)
         losses = torch.zeros(2, device=dev)
         d_pbw, d_tbw = e(m, 24), e(m, 24)
         _lib.check(L.aninerf_bw_loss(_lib.ptr(pbw), _lib.ptr(tbw), _lib.ptr(sel), _lib.ptr(n_sel), m, _lib.ptr(losses[0:1]), _lib.ptr(d_pbw),
@@ -314,9 +355,39 @@ class TrainStep:
         d_rgb_map = e(R, 3)
         _lib.check(L.aninerf_img_loss(_lib.ptr(rgb_map), _lib.ptr(rgb_gt), _lib.ptr(mask), R, _lib.ptr(losses[1:2]), _lib.ptr(d_rgb_map), st))
 
+        self._keep_loss = (rgb_gt, mask)
+        return losses, d_rgb_map, d_pbw, d_tbw
+
+    @torch.no_grad()
+    def backward_pass(self, s, d_rgb_map, d_pbw, d_tbw):
+        """d loss / d parameter for gradients arriving on rgb_map (R,3), pbw (m,24) and tbw (m,24) of forward pass `s`
+        (d_pbw is updated in place).  Returns the step's _Grads (its flat buffer is overwritten by the next backward pass)."""
+        if s['gen'] != self._generation:
+            raise _lib.AninerfError('backward of a stale forward pass: the training step keeps ONE set of activation buffers, so a '
+                                    'forward pass must be followed by its backward before the next forward (no gradient accumulation '
+                                    'over several forwards)')
+        cfg, L = self.cfg, _lib.lib()
+        dev, m, n, R, S, sd, plan = s['dev'], s['m'], s['n'], s['R'], s['S'], s['sd'], s['plan']
+        st = _lib.stream_ptr(dev)
+        T.begin_step(dev)
+        G = plan['G']
+        G.flat.zero_()
+        trunk_p, trunk_c, trunk_n, d_pe_all = plan['trunk_p'], plan['trunk_c'], plan['trunk_n'], plan['d_pe']
+        latent_index, A, tvol, tb, lat_n = s['latent_index'], s['A'], s['tvol'], s['tb'], s['lat_n']
+        index, dists, tpts, raw, sigma_masked = s['index'], s['dists'], s['tpts'], s['raw'], s['sigma_masked']
+        h8p, h8c, h8n, init_p, init_t, pbw, tbw = s['h8p'], s['h8c'], s['h8n'], s['init_p'], s['init_t'], s['pbw'], s['tbw']
+        feat, f2, pe_v, hv = s['feat'], s['f2'], s['pe_v'], s['hv']
+        p = 'tpose_human.'
+        Wfc = _w2(sd['bw_fc.weight'])
+        Wa, Wf, Wl, Wv, Wr = (_w2(sd[p + k + '.weight']) for k in ('alpha_fc', 'feature_fc', 'latent_fc', 'view_fc', 'rgb_fc'))
+        white = s['white']
+
+        def e(*shape):
+            return torch.empty(*shape, device=dev)
+
         # ================================= backward =========================================================================
         d_raw = e(n, 4)
-        _lib.check(L.aninerf_composite_backward(_lib.ptr(raw), _lib.ptr(d_rgb_map), R, S, pr.white_bkgd, _lib.ptr(d_raw), st))
+        _lib.check(L.aninerf_composite_backward(_lib.ptr(raw), _lib.ptr(d_rgb_map), R, S, white, _lib.ptr(d_raw), st))
         d_sigma, d_rgb = e(m, 1), e(m, 3)
         _lib.check(L.aninerf_nerf_tail_backward(_lib.ptr(d_raw), _lib.ptr(raw), _lib.ptr(index), _lib.ptr(sigma_masked), _lib.ptr(tpts), _lib.ptr(tb),
                                                 _lib.ptr(dists), m, _lib.ptr(d_sigma), _lib.ptr(d_rgb), st))
@@ -367,35 +438,78 @@ class TrainStep:
         T.gemm([(Op(d_delta), Op(Wfc).T)], trunk_p.dz[0][:m], relu_mask=h8p)
         trunk_p.backward(m, g_bw_lat[latent_index + 1:latent_index + 2], False)
 
-        selb = sel.bool()
-        ret = {'rgb_map': rgb_map.view(1, R, 3), 'acc_map': acc_map.view(1, R), 'depth_map': depth_map.view(1, R), 'raw': raw.view(1, n, 4),
-               'pbw': pbw[selb].view(1, -1, 24), 'tbw': tbw[selb].view(1, -1, 24)}
-        stats = {'bw_loss': losses[0], 'img_loss': losses[1], 'loss': losses[0] + losses[1]}
-        self._keep = (keep, o, d, near, far, tr, A, pvol, tvol, pb, tb, rgb_gt, mask)
         T.end_step(dev)
-        return ret, stats, G
+        return G
+
+def _param_views(flat, shapes):
+    out, off = [], 0
+    for sh in shapes:
+        k = 1
+        for v in sh:
+            k *= v
+        out.append(flat[off:off + k].view(sh))
+        off += k
+    return out
 
 
 class _LossFn(torch.autograd.Function):
-    """Carries the kernel-computed gradients into torch.autograd: loss.backward() adds g * dloss/dparam to param.grad."""
+    """Carries the kernel-computed gradients into torch.autograd: loss.backward() adds g * dloss/dparam to param.grad.
+    The step's flat gradient buffer is scratch that the next step overwrites, so forward keeps its own copy (5 MB): a second
+    forward before this loss's backward (validation between forward and backward, several losses alive) cannot corrupt it."""
 
     @staticmethod
     def forward(ctx, loss, flat_grad, *params):
-        ctx.flat = flat_grad
+        ctx.flat = flat_grad.clone()
         ctx.shapes = [p.shape for p in params]
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
         scaled = ctx.flat * g                      # ONE kernel for all 46 tensors; the per-parameter gradients are views of it
-        out, off = [], 0
-        for s in ctx.shapes:
-            k = 1
-            for v in s:
-                k *= v
-            out.append(scaled[off:off + k].view(s))
-            off += k
-        return (None, None, *out)
+        return (None, None, *_param_views(scaled, ctx.shapes))
+
+
+class _RenderFn(torch.autograd.Function):
+    """`Renderer.render` in training mode as ONE autograd node: forward = TrainStep.forward_pass, backward =
+    TrainStep.backward_pass for gradients arriving on rgb_map, pbw and tbw -- the three outputs the reference's losses read
+    (tpose_trainer.py:48-63).  acc_map / depth_map / raw are returned without a graph (no reference loss uses them)."""
+
+    @staticmethod
+    def forward(ctx, step, batch, t_rand, *params):
+        s = step.forward_pass(batch, t_rand)
+        ret = TrainStep.contract(s)
+        ctx.step, ctx.state = step, s
+        ctx.shapes = [p.shape for p in params]
+        ctx.mark_non_differentiable(ret['acc_map'], ret['depth_map'], ret['raw'])
+        return ret['rgb_map'], ret['acc_map'], ret['depth_map'], ret['raw'], ret['pbw'], ret['tbw']
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, g_depth, g_raw, g_pbw, g_tbw):
+        s = ctx.state
+        dev, m, R = s['dev'], s['m'], s['R']
+        selb = s['sel'].bool()
+        d_rgb = _lib.f32c(g_rgb.reshape(R, 3)) if g_rgb is not None else torch.zeros(R, 3, device=dev)
+        d_pbw, d_tbw = torch.zeros(m, 24, device=dev), torch.zeros(m, 24, device=dev)
+        if g_pbw is not None:
+            d_pbw[selb] = g_pbw.reshape(-1, 24)
+        if g_tbw is not None:
+            d_tbw[selb] = g_tbw.reshape(-1, 24)
+        G = ctx.step.backward_pass(s, d_rgb, d_pbw, d_tbw)
+        return (None, None, None, *_param_views(G.flat.clone(), ctx.shapes))
+
+
+def render_with_grad(renderer, batch, t_rand=None):
+    """tpose_renderer.Renderer.render when a gradient is required (tpose_renderer.py:154-155 keeps the device tensors and their
+    graph): the reference's own `NetworkWrapper` (lib/train/trainers/tpose_trainer.py:21-73) can sit on the drop-in renderer."""
+    cfg, net = renderer.cfg, renderer.net
+    step = renderer.__dict__.get('_train_step')
+    if step is None:
+        step = renderer.__dict__['_train_step'] = TrainStep(net, cfg)
+    if t_rand is None and config.get(cfg, 'perturb') > 0. and net.training:
+        t_rand = torch.rand(1, batch['ray_o'].shape[1], int(config.get(cfg, 'N_samples')))     # CPU generator, tpose_renderer.py:35
+    params = [p for _, p in net.named_parameters()]
+    rgb_map, acc_map, depth_map, raw, pbw, tbw = _RenderFn.apply(step, batch, t_rand, *params)
+    return {'rgb_map': rgb_map, 'acc_map': acc_map, 'depth_map': depth_map, 'raw': raw, 'pbw': pbw, 'tbw': tbw}
 
 
 class NetworkWrapper(nn.Module):
@@ -410,7 +524,9 @@ class NetworkWrapper(nn.Module):
 
     def forward(self, batch, t_rand=None):
         cfg = self.cfg
-        if t_rand is None and config.get(cfg, 'perturb') > 0. and self.net.training:
+        if not (torch.is_grad_enabled() and self.net.training):
+            return self._forward_eval(batch)
+        if t_rand is None and config.get(cfg, 'perturb') > 0.:
             R = batch['ray_o'].shape[1]
             t_rand = torch.rand(1, R, int(config.get(cfg, 'N_samples')))       # CPU generator, as tpose_renderer.py:35
         ret, stats, G = self.__dict__['_step'].run(batch, t_rand)
@@ -418,6 +534,26 @@ class NetworkWrapper(nn.Module):
         loss = _LossFn.apply(stats['loss'], G.flat, *params)
         scalar_stats = {'bw_loss': stats['bw_loss'], 'img_loss': stats['img_loss'], 'loss': loss}
         return ret, loss, scalar_stats, {}
+
+    @torch.no_grad()
+    def _forward_eval(self, batch):
+        """Validation (Trainer.val, lib/train/trainers/trainer.py:84-115: eval mode, no_grad, a whole mask_at_box image of ~1e5
+        rays): the fused render path -- chunk-safe, no activation plan, no backward kernels -- plus the two losses."""
+        import torch.nn.functional as F
+        r = self.renderer
+        out = r.render_device(batch, want_bw=True)
+        sel, n_sel = r.select_rows(out)
+        k = int(n_sel.item())
+        pbw, tbw = r.gather_selected(out, sel, k)
+        R = batch['ray_o'].shape[1]
+        S = int(config.get(self.cfg, 'N_samples'))
+        ret = {'rgb_map': out['rgb_map'].view(1, R, 3), 'acc_map': out['acc_map'].view(1, R), 'depth_map': out['depth_map'].view(1, R),
+               'raw': out['raw'].view(1, R * S, 4), 'pbw': pbw.view(1, k, 24), 'tbw': tbw.view(1, k, 24)}
+        bw_loss = F.smooth_l1_loss(ret['pbw'], ret['tbw'])
+        mask = batch['mask_at_box'].reshape(1, R).bool()
+        img_loss = torch.mean((ret['rgb_map'][mask] - batch['rgb'].reshape(1, R, 3)[mask]) ** 2)
+        loss = bw_loss + img_loss
+        return ret, loss, {'bw_loss': bw_loss, 'img_loss': img_loss, 'loss': loss}, {}
 
 
 def allreduce_gradients(net, world_size: int, group=None):
@@ -443,7 +579,9 @@ def train_iteration(wrapper: NetworkWrapper, batch, optimizer, world_size: int =
     """One iteration of Trainer.train (trainer.py:62-66) -- zero_grad, forward, backward, [DDP mean], clip_grad_value_(40), step --
     without the round trip through torch.autograd: the step's flat gradient buffer IS the all-reduce payload (one NCCL all-reduce
     of 1 274 652 floats), is clipped with one kernel, and its per-parameter views become `.grad`.  Same numbers as
-    `loss.backward()` on `NetworkWrapper.forward` (tests/test_gpu_train.py), ~1 ms less host time per iteration."""
+    `loss.backward()` on `NetworkWrapper.forward` (tests/test_gpu_train.py), ~1 ms less host time per iteration.
+    NOTE: after this call every `p.grad` is a VIEW of the step's flat gradient buffer -- scratch memory that the next
+    `train_iteration` / `NetworkWrapper.forward` zeroes and overwrites.  Read or copy gradients before the next step."""
     cfg = wrapper.cfg
     if t_rand is None and config.get(cfg, 'perturb') > 0. and wrapper.net.training:
         t_rand = torch.rand(1, batch['ray_o'].shape[1], int(config.get(cfg, 'N_samples')))

@@ -366,6 +366,12 @@ int aninerf_img_loss(const float *rgb_map, const float *rgb_gt, const uint8_t *m
 /* alpha_ind of tpose_nerf_network.py:192-194 for every chunk: sigma_masked > train_th plus the chunk's first arg-max row. */
 int aninerf_select_rows(const float *sigma_masked, const int32_t *chunk_offsets, int32_t n_chunks, float train_th, uint8_t *sel,
                         int32_t *n_sel, void *stream);
+/* The boolean-mask gathers `pbw[alpha_ind]`, `tbw[alpha_ind]` of tpose_nerf_network.py:195-196 for every chunk at once: the rows
+ * of src_a / src_b (24 floats each, 16-byte aligned) whose `sel` byte is set, in ascending row order, packed into dst_a / dst_b
+ * (src_b / dst_b may be NULL).  sel_offsets: (n_chunks + 1) int32 scratch; on return [c] = first output row of chunk c and
+ * [n_chunks] = total selected rows (stays on the device).  dst must have room for chunk_offsets[n_chunks] rows. */
+int aninerf_gather_selected_rows(const uint8_t *sel, const int32_t *chunk_offsets, int32_t n_chunks, const float *src_a,
+                                 const float *src_b, float *dst_a, float *dst_b, int32_t *sel_offsets, void *stream);
 /* bw_loss = smooth_l1(pbw[sel], tbw[sel]) (tpose_trainer.py:48-51) and its gradients (n,24), zero on unselected rows. */
 int aninerf_bw_loss(const float *pbw, const float *tbw, const uint8_t *sel, const int32_t *n_sel, int64_t n, float *loss, float *d_pbw,
                     float *d_tbw, void *stream);

@@ -303,14 +303,17 @@ def network_forward(sd, wpts, viewdir, dists, batch, cfg, return_debug=False):
     rgb_s = torch.sigmoid(rgb[0])
     a = 1. - torch.exp(-F.relu(alpha[0]) * dists)
     raw = torch.cat((rgb_s, a[None]), dim=0).transpose(0, 1)
-    raw_full = torch.zeros([1, wpts.shape[1], 4], dtype=wpts.dtype)
+    raw_full = torch.zeros([1, wpts.shape[1], 4], dtype=wpts.dtype, device=wpts.device)
     raw_full[pind] = raw
     ret = {'pbw': pbw_sel, 'tbw': tbw_sel, 'raw': raw_full}
-    if return_debug:
+    if return_debug == 'light':
+        # full-size frames: only what the row-selection / active-set checks need (no per-sample (n,25) tensors)
+        ret['_debug'] = {'pind': pind[0], 'sigma_masked': alpha[0], 'alpha_ind': alpha_ind[0], 'tpose': tpose[0]}
+    elif return_debug:
         ret['_debug'] = {'pind': pind[0], 'pnorm': pnorm[0], 'pose_pts': pose_pts[0], 'tpose': tpose[0],
                          'pbw_all': pbw[0].transpose(0, 1), 'tbw_all': tbw[0].transpose(0, 1),
                          'init_pbw': init_pbw[0].transpose(0, 1), 'sigma': sigma_raw[0], 'rgb_raw': rgb[0].transpose(0, 1),
-                         'outside': outside[0], 'alpha_ind': alpha_ind[0]}
+                         'outside': outside[0], 'alpha_ind': alpha_ind[0], 'sigma_masked': alpha[0]}
     return ret
 
 
@@ -373,8 +376,9 @@ def render(sd, batch, cfg=None, t_rand=None, return_debug=False, grad=False):
                   'pbw': ret['pbw'].view(nb, -1, 24), 'tbw': ret['tbw'].view(nb, -1, 24)}
             if return_debug:
                 o_['_debug'] = ret['_debug']
-                o_['_debug']['z_vals'] = z[0]
-                o_['_debug']['wpts'] = pts[0]
+                if return_debug != 'light':
+                    o_['_debug']['z_vals'] = z[0]
+                    o_['_debug']['wpts'] = pts[0]
             outs.append(o_)
     out = {k: torch.cat([r[k] for r in outs], dim=1) for k in outs[0] if k != '_debug'}
     if return_debug:
@@ -502,7 +506,7 @@ def render_mmsk(sd, batch, cfg=None, return_debug=False):
             pts, z = sample_points(o, d, near[:, i:i + cfg.chunk], far[:, i:i + cfg.chunk], S)
             nb, npix = pts.shape[:2]
             inside = inside_all_views(pts.view(nb, -1, 3), batch).view(-1)
-            full_raw = torch.zeros([nb * npix * S, 4])
+            full_raw = torch.zeros([nb * npix * S, 4], device=pts.device)
             n_act = 0
             if inside.sum() > 0:
                 w = pts.view(-1, 3)[inside]

@@ -1,0 +1,222 @@
+"""GPU parity at the sizes BASELINE.json states (configs 2, 3, 5) and on a trained-like NeRF field -- the CUDA path against
+the CPU ORACLE on the whole workload (the oracle renders a 1024x1024 frame in a few seconds on the box's host cores), not
+through self-consistency properties.
+
+Gates (north_star): active set / masks bit-exact; blend weights and canonical points <= 1e-5; rgb / acc / depth <= 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, check_selected_rows, to_device
+from animatable_nerf_b200 import host_geometry, synthetic
+
+pytestmark = pytest.mark.gpu
+
+BW_TOL = 1e-5
+RGB_TOL = 2e-3
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'these tests need the B200'
+    return torch.device('cuda:0')
+
+
+def _renderer(dev, sd, **over):
+    from animatable_nerf_b200 import config
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer import Renderer
+    cfg = config.make_cfg(perturb=0., **over)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    return Renderer(net.to(dev).eval(), cfg)
+
+
+def _maps_err(dv, ref):
+    return {k: float((dv[k].reshape(-1).cpu() - ref[k].reshape(-1)).abs().max()) for k in ('rgb_map', 'acc_map', 'depth_map')}
+
+
+@pytest.fixture(scope='module')
+def frame_c2():
+    """BASELINE config 2: the bench frame (seeds: body 1, pose 2; 2.5 cm volumes) and its 1024x1024 camera."""
+    frame = synthetic.make_frame(pose_seed=2, body_seed=1, voxel=0.025, latent_index=0)
+    K, R, T = synthetic.make_camera(frame, 1024, 1024, focal=1070.0)
+    return frame, (K, R, T)
+
+
+def test_config2_whole_frame_full_contract_vs_oracle(dev, frame_c2):
+    """aninerf_313, the WHOLE 1024x1024 frame (242 907 box-hitting rays x 64 = 15.5 M samples, 119 chunks) in the package's
+    default mode (full contract: posed + canonical blend-weight field + NeRF, dense raw, pbw / tbw rows):
+      * stage 1 (rays, near / far, mask_at_box) bit-exact;
+      * the active set (zero pattern of raw = pnorm mask + per-chunk argmin forcing) bit-exact over all 15.5 M samples;
+      * rgb / acc / depth / raw within 2e-3;
+      * the pbw / tbw row set vs the oracle's (mismatches only inside the sigma noise), common rows within 1e-5;
+      * the render-only mode composites to the same maps."""
+    from animatable_nerf_b200 import frontend
+    frame, (K, R, T) = frame_c2
+    ro, rd, near, far, mask = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    o_ro, o_rd, o_near, o_far, o_mask = O.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'])
+    assert np.array_equal(mask.cpu().numpy(), o_mask)
+    for a, b in ((ro, o_ro), (rd, o_rd), (near, o_near), (far, o_far)):
+        assert np.array_equal(a.cpu().numpy(), b)
+    n = o_ro.shape[0]
+    assert 200_000 < n < 300_000
+    sd = synthetic.make_state_dict(seed=0)
+    batch = synthetic.make_render_batch(frame, o_ro, o_rd, o_near, o_far)
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0.), return_debug='light')
+    dbg = ref['_debug']
+    r = _renderer(dev, sd)
+    b = to_device(batch, dev)
+    dv = r.render_device(b, want_bw=True)
+    n_active = int(dv['n_active'].item())
+    assert n_active == int(dbg['pind'].sum())
+    assert np.array_equal(dv['active_index'][:n_active].cpu().numpy(), np.nonzero(dbg['pind'].numpy())[0].astype(np.int32))
+    assert np.array_equal(np.diff(dv['chunk_offsets'].cpu().numpy()), dbg['chunk_active'].numpy())
+    err = _maps_err(dv, ref)
+    raw_err = float((dv['raw'].cpu() - ref['raw'][0]).abs().max())
+    print('config 2 whole frame:', n, 'rays', n_active, 'active; max abs error', err, 'raw', raw_err)
+    assert max(err.values()) <= RGB_TOL and raw_err <= RGB_TOL
+    # canonical points <= 1e-5 is implied by tbw <= 1e-5 on every common row below (tbw is sampled at those points)
+    rows, cg, ref_rows, cr, pbw, tbw, n_mism = check_selected_rows(r, dv, dbg)
+    print('selected rows', rows.numel(), 'oracle', ref_rows.numel(), 'one-sided', n_mism)
+    assert n_mism <= 1e-3 * ref_rows.numel() + 8
+    assert float((pbw[cg] - ref['pbw'][0][cr]).abs().max()) <= BW_TOL
+    assert float((tbw[cg] - ref['tbw'][0][cr]).abs().max()) <= BW_TOL
+    # render-only (the mode the headline times): same maps from the compact rows
+    ro_mode = r.render_device(b, want_bw=False)
+    assert max(_maps_err(ro_mode, ref).values()) <= RGB_TOL
+    # Renderer.render(batch): the public call returns the same numbers on the host
+    out = r.render(b)
+    assert out['raw'].shape == ref['raw'].shape and out['pbw'].shape[1] == rows.numel()
+    assert torch.equal(out['rgb_map'].reshape(-1, 3), dv['rgb_map'].cpu())
+
+
+def test_config3_whole_frame_novel_pose_vs_oracle(dev, frame_c2):
+    """aninerf_s9p shapes (num_train_frame 260, num_eval_frame 133), novel-pose blend-weight field, the WHOLE 1000x1000 frame
+    (f = 1150): active set bit-exact, rgb / acc / depth within 2e-3 of the oracle."""
+    frame, _ = frame_c2
+    K, R, T = synthetic.make_camera(frame, 1000, 1000, focal=1150.0)
+    ro, rd, near, far, mask = O.get_rays_within_bounds(1000, 1000, K, R, T, frame['wbounds'])
+    n = ro.shape[0]
+    assert n > 250_000
+    sd = synthetic.make_state_dict(seed=1, num_train_frame=260, num_eval_frame=133)
+    batch = synthetic.make_render_batch(frame, ro, rd, near, far)
+    batch['bw_latent_index'] = torch.tensor([7])
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0., test_novel_pose=True), return_debug='light')
+    r = _renderer(dev, sd, b200_render_only=True, aninerf_animation=True, test_novel_pose=True, num_train_frame=260, num_eval_frame=133)
+    dv = r.render_device(to_device(batch, dev), want_bw=False, keep_raw=True)
+    n_active = int(dv['n_active'].item())
+    assert n_active == int(ref['_debug']['pind'].sum())
+    active_gpu = (dv['raw'][:, :3] != 0).any(-1).cpu()           # sigmoid(rgb) > 0 exactly on the evaluated samples
+    assert torch.equal(active_gpu, ref['_debug']['pind'])
+    err = _maps_err(dv, ref)
+    print('config 3 whole frame:', n, 'rays', n_active, 'active; max abs error', err)
+    assert max(err.values()) <= RGB_TOL
+    assert float((dv['raw'].cpu() - ref['raw'][0]).abs().max()) <= RGB_TOL
+
+
+def test_config5_density_grid_chunks_of_131072(dev, frame_c2):
+    """vis_posed_mesh density query with the chunk size the path uses (2048 * 64 = 131 072 points,
+    aninerf_mesh_renderer.py:35): a 256 x 256 x 16 slab of the 256^3 grid over wbounds = 8 full chunks.  Mask (norm_th 0.1 +
+    per-chunk argmin forcing) bit-exact, sigma within 5e-3 (bf16 NeRF trunk) of the oracle's calculate_alpha per chunk."""
+    from animatable_nerf_b200 import config, sweep
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    frame, _ = frame_c2
+    sd = synthetic.make_state_dict(seed=0)
+    cfg = config.make_cfg(perturb=0., b200_render_only=True)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    wb = np.asarray(frame['wbounds'], dtype=np.float64)
+    vs = ((wb[1] - wb[0]) / 255.0).tolist()
+    pts = sweep.grid_points(frame['wbounds'], vs, dev)[:256, :256, :256]
+    z0 = 120                                                       # a slab through the body
+    slab = pts[:, :, z0:z0 + 16].contiguous()
+    assert slab.shape[:3] == (256, 256, 16)
+    fb = synthetic.collate_frame(frame, dev)
+    cube = sweep.query_density_grid(net, fb, slab, None, chunk=sweep.GRID_CHUNK)
+    flat = slab.reshape(-1, 3).cpu()
+    assert flat.shape[0] == 8 * sweep.GRID_CHUNK
+    cb = synthetic.collate_frame(frame)
+    ref = torch.cat([O.calculate_alpha(sd, flat[i:i + sweep.GRID_CHUNK], cb, O.OracleCfg()) for i in range(0, flat.shape[0], sweep.GRID_CHUNK)])
+    got = cube.reshape(-1).cpu()
+    assert np.array_equal((got != 0).numpy(), (ref != 0).numpy())
+    n_on = int((ref != 0).sum())
+    assert n_on > 10_000
+    err = float((got - ref).abs().max())
+    print('config 5 grid slab: evaluated points', n_on, 'max |sigma - oracle|', err)
+    assert err <= 5e-3
+
+
+def test_config5_two_views_of_the_1024_sweep(dev, frame_c2):
+    """Two views of the 64-view circular sweep at 1024 x 1024 (gen_path orbit; on-device ray generation + box intersection +
+    compaction + render + scatter through mask_at_box): every pixel within 2e-3 of the oracle's render of the same view."""
+    from animatable_nerf_b200 import config, sweep
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer import Renderer
+    frame, _ = frame_c2
+    sd = synthetic.make_state_dict(seed=0)
+    cfg = config.make_cfg(perturb=0., b200_render_only=True)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    rig = synthetic.make_camera_rig(frame, n_views=8)
+    path = host_geometry.circular_camera_path(list(rig), 64)
+    K = np.array([[1070., 0, 512.], [0, 1070., 512.], [0, 0, 1.]])
+    views = [path[5], path[37]]
+    fb = synthetic.collate_frame(frame, dev)
+    out = sweep.render_views(Renderer(net, cfg), fb, K, views, 1024, 1024)
+    for v, (rgb, acc, depth) in out.items():
+        RT = views[v]
+        ro, rd, near, far, mask = O.get_rays_within_bounds(1024, 1024, K, RT[:3, :3], RT[:3, 3:], frame['wbounds'])
+        assert mask.sum() > 100_000
+        ref = O.render(sd, synthetic.make_render_batch(frame, ro, rd, near, far), O.OracleCfg(perturb=0.))
+        m = torch.from_numpy(mask.reshape(-1))
+        e_rgb = float((rgb.reshape(-1, 3).cpu()[m] - ref['rgb_map'][0]).abs().max())
+        e_acc = float((acc.reshape(-1).cpu()[m] - ref['acc_map'][0]).abs().max())
+        e_dep = float((depth.reshape(-1).cpu()[m] - ref['depth_map'][0]).abs().max())
+        print('sweep view', v, 'rays', int(mask.sum()), 'max abs error rgb/acc/depth', e_rgb, e_acc, e_dep)
+        assert max(e_rgb, e_acc, e_dep) <= RGB_TOL
+        assert float(acc.reshape(-1).cpu()[~m].abs().max()) == 0.0
+
+
+def trained_like_state_dict(seed=0, gain=1.6, alpha_gain=8.0, alpha_bias=5.0):
+    """A NeRF field with the statistics of a TRAINED one rather than of the default init: every layer's weights x 1.6
+    (activations ~40x larger after 8 layers), a density head scaled x 8 with a positive bias, so that sigma spans [0, ~8] and
+    acc_map exceeds 0.5 on the body rays -- the regime where the 2e-3 gate on rgb / acc / depth is NOT vacuous (at random
+    init sigma ~ +-0.1 and acc ~ 1e-2).  The blend-weight fields keep the default init (their sharper-weights case is
+    tests/test_gpu_stages.py::test_blend_weight_field_sharper_weights)."""
+    sd = synthetic.make_state_dict(seed=seed, gain=1.0)
+    sharp = synthetic.make_state_dict(seed=seed, gain=gain)
+    for k in sd:
+        if k.startswith('tpose_human.') and not k.endswith('nf_latent.weight'):
+            sd[k] = sharp[k]
+    sd['tpose_human.alpha_fc.weight'] = sd['tpose_human.alpha_fc.weight'] * alpha_gain
+    sd['tpose_human.alpha_fc.bias'] = torch.full_like(sd['tpose_human.alpha_fc.bias'], alpha_bias)
+    return sd
+
+
+@pytest.mark.parametrize('precision', [1, 3])
+def test_trained_like_nerf_field_margin(dev, precision):
+    """The bf16 NeRF field (b200_nerf_precision 1, the default) and its bf16x3 fallback (3) on a trained-like field: the
+    measured margin to the 2e-3 gate is printed; both must hold it.  (CPU emulation of the single-pass kernel arithmetic on
+    this case predicts rgb 2.7e-4, acc 3.6e-4, depth 1.3e-3.)"""
+    from helpers import small_frame_case
+    _, _, batch, _ = small_frame_case(voxel=0.05, H=192, W=192, focal=205.0)
+    sd = trained_like_state_dict()
+    ref = O.render(sd, batch, O.OracleCfg(perturb=0.), return_debug='light')
+    acc = ref['acc_map'][0]
+    assert float((acc > 0.5).float().mean()) > 0.1 and float(acc.max()) > 0.95, 'the case must have opaque body rays'
+    r = _renderer(dev, sd, b200_nerf_precision=precision)
+    dv = r.render_device(to_device(batch, dev), want_bw=True)
+    n_active = int(dv['n_active'].item())
+    assert n_active == int(ref['_debug']['pind'].sum())
+    err = _maps_err(dv, ref)
+    sig_err = float((dv['sigma_masked'][:n_active].cpu() - ref['_debug']['sigma_masked']).abs().max())
+    print(f'trained-like NeRF field, precision {precision}: max abs error {err}, sigma {sig_err} (sigma range '
+          f'[{float(ref["_debug"]["sigma_masked"].min()):.2f}, {float(ref["_debug"]["sigma_masked"].max()):.2f}]); '
+          f'margin to the 2e-3 gate x{RGB_TOL / max(err.values()):.1f}')
+    assert max(err.values()) <= RGB_TOL
+    if precision == 3:
+        assert max(err.values()) <= 2e-4 and sig_err <= 5e-4

@@ -152,3 +152,39 @@ def test_composite_backward(dev):
         _lib.check(_lib.lib().aninerf_composite_backward(_lib.ptr(raw_d), _lib.ptr(gmap_d), R, S, int(white), _lib.ptr(d_raw),
                                                          _lib.stream_ptr(dev)))
         assert _rel(d_raw.cpu(), r.grad) <= 1e-5
+
+
+def test_select_and_gather_rows_match_per_chunk_loop(dev):
+    """aninerf_select_rows + aninerf_gather_selected_rows == `alpha_ind` / `pbw[alpha_ind]` of tpose_nerf_network.py:192-196
+    evaluated chunk by chunk: threshold, first arg-max forced (ties, single-row and all-below-threshold chunks), ascending rows."""
+    import ctypes as C
+    from animatable_nerf_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(2)
+    counts = torch.tensor([5, 1, 40, 7, 3, 0, 700, 2048, 1])
+    off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]).int()
+    n = int(counts.sum())
+    sig = torch.randn(n, generator=g)
+    sig[5] = -3.0                      # single-row chunk below the threshold: must still be kept
+    sig[6:46] = -1.0                   # a whole chunk below threshold with ties: first row wins
+    want = sig > 0
+    for c in range(len(counts)):
+        a, b = int(off[c]), int(off[c + 1])
+        if b > a:
+            want[a + int(torch.argmax(sig[a:b]))] = True
+    a24, b24 = torch.randn(n, 24, generator=g), torch.randn(n, 24, generator=g)
+    d_sig, d_off, d_a, d_b = sig.to(dev), off.to(dev), a24.to(dev), b24.to(dev)
+    sel = torch.zeros(n, dtype=torch.uint8, device=dev)
+    n_sel = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = _lib.stream_ptr(dev)
+    _lib.check(L.aninerf_select_rows(_lib.ptr(d_sig), _lib.ptr(d_off), len(counts), 0.0, _lib.ptr(sel), _lib.ptr(n_sel), st))
+    assert torch.equal(sel.bool().cpu(), want) and int(n_sel.item()) == int(want.sum())
+    k = int(want.sum())
+    o_a, o_b = torch.empty(k, 24, device=dev), torch.empty(k, 24, device=dev)
+    offs = torch.empty(len(counts) + 1, dtype=torch.int32, device=dev)
+    _lib.check(L.aninerf_gather_selected_rows(_lib.ptr(sel), _lib.ptr(d_off), len(counts), _lib.ptr(d_a), _lib.ptr(d_b), _lib.ptr(o_a), _lib.ptr(o_b),
+                                              _lib.ptr(offs), st))
+    assert torch.equal(o_a.cpu(), a24[want]) and torch.equal(o_b.cpu(), b24[want])
+    assert int(offs[-1].item()) == k
+    per_chunk = [int(want[int(off[c]):int(off[c + 1])].sum()) for c in range(len(counts))]
+    assert offs[:-1].cpu().tolist() == [sum(per_chunk[:c]) for c in range(len(counts))]

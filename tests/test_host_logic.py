@@ -5,7 +5,6 @@ import torch
 from helpers import O, golden_small_case
 from animatable_nerf_b200 import config, ray_tiles, synthetic, weights
 from animatable_nerf_b200.tpose_nerf_network import Network
-from animatable_nerf_b200.tpose_renderer import select_forced_argmax
 
 
 def _run_layers(layers, x, final_relu):
@@ -67,21 +66,6 @@ def test_nerf_field_folding_matches_oracle():
         c = v @ rw.T + rb
         assert np.abs(a[:, 0] - alpha[0, 0].double().numpy()).max() < 1e-5
         assert np.abs(c.T - rgb[0].double().numpy()).max() < 1e-5
-
-
-def test_select_forced_argmax_matches_per_chunk_loop():
-    g = torch.Generator().manual_seed(2)
-    counts = torch.tensor([5, 1, 40, 7, 3])
-    off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]).int()
-    sig = torch.randn(int(counts.sum()), generator=g)
-    sig[5] = -3.0                      # single-row chunk below the threshold: must still be kept
-    sig[6:46] = -1.0                   # a whole chunk below threshold with ties: first row wins
-    got = select_forced_argmax(sig, off, 0.0)
-    want = sig > 0
-    for c in range(len(counts)):
-        a, b = int(off[c]), int(off[c + 1])
-        want[a + int(torch.argmax(sig[a:b]))] = True
-    assert torch.equal(got, want)
 
 
 def test_ray_tiles_partition_is_a_permutation_aligned_to_chunks():
