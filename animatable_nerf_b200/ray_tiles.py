@@ -115,3 +115,42 @@ class PeerImage:
         assert n_rays <= self.capacity
         self.hdls[slot].barrier(0, 10000)
         return self.bufs[slot][:n_rays * 5].view(n_rays, 5)
+
+
+class PeerVolume:
+    """Sharded host->device upload of a frame's replicated volume (`pbw`, 18 MB at 2.5 cm): every rank needs the whole volume, but
+    each rank's PCIe link only carries 1/world of it -- rank r copies slice r from (pinned) host memory into its own buffer and
+    pushes it into every peer's buffer over NVLink (peer-mapped symmetric memory, the same pattern as the image gather); one
+    barrier completes the volume everywhere.  Two buffers alternate (a slow rank may still sample frame k while a fast one
+    uploads frame k+1)."""
+
+    def __init__(self, capacity_floats: int, rank: int, world: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.capacity = rank, world, int(capacity_floats)
+        group = group if group is not None else dist.group.WORLD
+        self.bufs = [symm.empty(self.capacity, dtype=torch.float32, device=device) for _ in range(2)]
+        self.hdls = [symm.rendezvous(b, group) for b in self.bufs]
+        self.peers = [[h.get_buffer(p, (self.capacity,), torch.float32, 0) for p in range(world)] for h in self.hdls]
+        self.turn = 0
+
+    def slice_of(self, n: int, rank: int):
+        per = ((n + self.world - 1) // self.world + 3) // 4 * 4
+        return min(n, rank * per), min(n, (rank + 1) * per)
+
+    def upload(self, host_vol: torch.Tensor) -> torch.Tensor:
+        """host_vol: float32 host tensor (pinned for an asynchronous copy), identical on every rank.  Returns the device copy
+        (a view of this rank's symmetric buffer, valid until the upload after next)."""
+        n = host_vol.numel()
+        assert n <= self.capacity
+        slot = self.turn
+        self.turn ^= 1
+        flat = host_vol.reshape(-1)
+        a, b = self.slice_of(n, self.rank)
+        mine = self.bufs[slot][a:b]
+        if b > a:
+            mine.copy_(flat[a:b], non_blocking=True)                       # 1/world of the volume over this GPU's PCIe link
+            for p in range(self.world):
+                if p != self.rank:
+                    self.peers[slot][p][a:b].copy_(mine, non_blocking=True)    # NVLink push into the peer's buffer
+        self.hdls[slot].barrier(0, 10000)
+        return self.bufs[slot][:n].view(host_vol.shape)

@@ -39,6 +39,24 @@ class Renderer:
         return self._t_vals[key]
 
     # ---------------------------------------------------------------------------------------
+    FRAME_KEYS_RENDER = ('A', 'R', 'Th', 'pbw', 'pbounds', 'tbounds', 'wbounds', 'latent_index', 'bw_latent_index', 'ray_o', 'ray_d', 'near', 'far',
+                         'msks', 'Ks', 'RT', 'H', 'W')
+
+    def to_device(self, batch, device=None, non_blocking=True):
+        """Host batch -> device batch (the `batch[k] = batch[k].cuda()` loop of run.py:63-66), moving only the keys the
+        configured mode READS: in render-only mode (`b200_render_only`) the canonical volume `tbw` (11 MB per frame), `occupancy`,
+        `rgb`, ... never reach a kernel and stay on the host.  Pinned host tensors are copied asynchronously on the current
+        stream."""
+        dev = device if device is not None else next(self.net.parameters()).device
+        render_only = bool(config.get(self.cfg, 'b200_render_only'))
+        out = {}
+        for k, v in batch.items():
+            if torch.is_tensor(v) and (not render_only or k in self.FRAME_KEYS_RENDER):
+                out[k] = v.to(dev, non_blocking=non_blocking)
+            elif not torch.is_tensor(v):
+                out[k] = v
+        return out
+
     @torch.no_grad()
     def render_device(self, batch, t_rand=None, want_bw=None, silhouettes=None, peers=None, keep_raw=False):
         """The fused path, results left on the device.  Returns a dict with rgb_map/acc_map/depth_map

@@ -157,7 +157,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': f'{CPU_SAMPLE_RAYS} rays (every k-th ray of the frame) x 64 samples per step: 16 reference chunks of the same frame'},
+        'config': {'workload': WORKLOAD, 'sample': f'{CPU_SAMPLE_RAYS} rays (every k-th ray of the frame) x 64 samples per step: 16 reference chunks of the same frame',
+                   'mode': 'full contract (posed + canonical blend-weight field + NeRF, dense raw, pbw/tbw rows): the reference has no render-only '
+                           'mode -- compare with the B200 line\'s `full_contract` object, not with its render-only headline'},
         'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                          'sample': f'oracle/ port of Renderer.render on {CPU_SAMPLE_RAYS} rays x 64 samples, torch {torch.__version__} CPU, '
                                    f'{cores} threads, median of {max(1, args.steps)}'},
@@ -166,6 +168,35 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+def eager_cuda_rate(frame, cam, sd, size, dev, n_rays=None):
+    """`other_baselines.reference_eager_cuda`: the reference algorithm as a user of the reference runs it on this GPU -- eager
+    PyTorch ops on CUDA tensors, 2048-ray chunks, per-chunk boolean indexing (tpose_nerf_network.py:139-215 over
+    tpose_renderer.py:159-186) -- via the oracle's restatement with every tensor on `dev`.  Whole frame, CUDA-event timed."""
+    from animatable_nerf_b200 import synthetic
+    from oracle import aninerf_oracle as O
+    K, R, T = cam
+    ray_o, ray_d, near, far, _ = O.get_rays_within_bounds(size, size, K, R, T, frame['wbounds'])
+    if n_rays is not None:
+        sl = np.linspace(0, ray_o.shape[0] - 1, n_rays).astype(np.int64)
+        ray_o, ray_d, near, far = ray_o[sl], ray_d[sl], near[sl], far[sl]
+    batch = synthetic.make_render_batch(frame, ray_o, ray_d, near, far, device=dev)
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    cfg = O.OracleCfg(perturb=0.)
+    warm = {k: (v[:, :4096] if k in ('ray_o', 'ray_d', 'near', 'far', 'occupancy') else v) for k, v in batch.items()}
+    O.render(sdd, warm, cfg)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = O.render(sdd, batch, cfg)
+    host = {k: v.cpu() for k, v in out.items()}          # tpose_renderer.py:154-155
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    n = batch['ray_o'].shape[1] * 64
+    del host, out
+    return n / (ms * 1e-3), ms, batch['ray_o'].shape[1]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -314,6 +345,28 @@ def other_configs(dev, frame, rank, world):
     ms = _time_ms(lambda: sweep.query_density_grid(net5, fb, pts, None, rank, world), reps=2, warm=1)
     out['config5_density_grid_256^3'] = {'ms': ms, 'points_per_s': pts.shape[0] * pts.shape[1] * pts.shape[2] / (ms * 1e-3),
                                          'grid': list(pts.shape[:3])}
+    # ---- active-fraction sweep: the headline frame at norm_th 0.05 (the reference's value) / 0.1 / 0.2.  FLOPs scale with the ACTIVE
+    # samples, nominal samples/s therefore falls as the shell around the body surface thickens ------------------------------------
+    K, R, T = synthetic.make_camera(frame, 1024, 1024)
+    ro, rd, near, far, _ = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    mine_f = ray_tiles.shard_batch(synthetic.make_render_batch(frame, ro, rd, near, far, device=dev), rank, world)
+    nf = ro.shape[0]
+    fsweep = {}
+    for th in (0.05, 0.1, 0.2):
+        rf = Renderer(net5, config.make_cfg(perturb=0., b200_render_only=True, norm_th=th))
+        na = rf.render_device(mine_f, want_bw=False)['n_active'].clone()
+        if world > 1:
+            dist.all_reduce(na)
+
+        def stepf():
+            o = rf.render_device(mine_f, want_bw=False)
+            maps = torch.cat([o['rgb_map'], o['acc_map'][:, None], o['depth_map'][:, None]], dim=1)
+            return ray_tiles.gather_maps(maps, nf, rank, world)
+        ms = _time_ms(stepf, reps=5, warm=1)
+        fsweep[f'norm_th_{th}'] = {'active_fraction': int(na.item()) / (nf * 64), 'ms_per_frame': ms, 'samples_per_s': nf * 64 / (ms * 1e-3),
+                                   'active_samples_per_s': int(na.item()) / (ms * 1e-3)}
+    out['active_fraction_sweep_1024x1024'] = fsweep
+    del mine_f
     rig = synthetic.make_camera_rig(frame, n_views=8)
     n_views = 8 * world
     path = host_geometry.circular_camera_path(list(rig), n_views)
@@ -365,7 +418,6 @@ def run_b200(args):
     mine = ray_tiles.shard_batch(full, rank, world)
     my_rays = mine['ray_o'].shape[1]
     host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in mine.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -375,15 +427,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # N > 1: the image gather is fused into the compositing kernel (stores into every rank's peer-mapped image over NVLink)
-    # followed by one symmetric-memory barrier; --gather nccl keeps the all_gather + reorder path for comparison
-    peer = None
+    # followed by one symmetric-memory barrier; --gather nccl keeps the all_gather + reorder path for comparison.
+    # The rendezvous must succeed on EVERY rank or on none: ranks on different gather paths would wait in different collectives.
+    peer, pvol = None, None
     if world > 1 and args.gather == 'peer':
+        ok = 1
         try:
             peer = ray_tiles.PeerImage(n_rays, rank, world, dev)
+            pvol = ray_tiles.PeerVolume(int(host['pbw'].numel()), rank, world, dev)
         except Exception as e:  # noqa: BLE001
+            ok = 0
+            print(f'bench: rank {rank}: symmetric memory unavailable ({e!r})', file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer, pvol = None, None
             if rank == 0:
-                print(f'bench: symmetric memory unavailable ({e!r}); using the NCCL all_gather path', file=sys.stderr)
-            peer = None
+                print('bench: using the NCCL all_gather path on all ranks', file=sys.stderr)
 
     def render_and_gather(b):
         if peer is not None:
@@ -397,34 +457,34 @@ def run_b200(args):
     def step_device():
         return render_and_gather(mine)
 
-    # e2e: the whole batch goes host -> device every step.  The keys the render-only path reads are copied on the compute
-    # stream, in the order the kernels need them; the rest of the batch (canonical volume `tbw`, occupancy, ... -- inputs of the
-    # training contract only) is copied on a side stream that is joined before the step ends, so its 11 MB overlap the kernels.
-    side = torch.cuda.Stream(device=dev)
+    # e2e: one frame through the public API from PINNED HOST buffers, host<->device copies inside the timed region.
+    #   N = 1: `renderer.to_device(batch)` (the keys the render-only mode reads; run.py:63-66 is the reference's loop) and
+    #          `renderer.render(batch)` -> host maps (one batched D->H copy into pinned memory + one sync);
+    #   N > 1: every rank uploads ITS rays and 1/N of the replicated blend-weight volume (ray_tiles.PeerVolume pushes the slice to
+    #          the peers over NVLink), renders its tiles with the fused peer gather, rank 0 downloads the image.
+    h2d_keys = [k for k, v in host.items() if torch.is_tensor(v) and k in renderer.FRAME_KEYS_RENDER]
+    h2d = sum(host[k].numel() * host[k].element_size() for k in h2d_keys)
+    if pvol is not None:
+        a_, b_ = pvol.slice_of(host['pbw'].numel(), rank)
+        h2d += (b_ - a_) * 4 - host['pbw'].numel() * 4
     pinned_out = torch.empty(n_rays, 5, dtype=torch.float32).pin_memory()
-    first = ('pbw', 'pbounds', 'R', 'Th', 'ray_o', 'ray_d', 'near', 'far', 'A', 'tbounds', 'latent_index', 'bw_latent_index')
 
     def step_e2e():
+        if world == 1:
+            return renderer.render(renderer.to_device(host, dev))
         main = torch.cuda.current_stream(dev)
-        b = {}
-        for k in first:
-            if k in host:
-                b[k] = host[k].to(dev, non_blocking=True) if torch.is_tensor(host[k]) else host[k]
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            for k, v in host.items():
-                if k not in b:
-                    b[k] = v.to(dev, non_blocking=True) if torch.is_tensor(v) else v
+        if pvol is not None:
+            b = renderer.to_device({k: v for k, v in host.items() if k != 'pbw'}, dev)
+            b['pbw'] = pvol.upload(host['pbw'])
+        else:
+            b = renderer.to_device(host, dev)
         out, img = render_and_gather(b)
-        main.wait_stream(side)
-        for k, v in b.items():
-            if torch.is_tensor(v):
-                v.record_stream(main)
-        res = img if rank == 0 else torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1)
-        dst = pinned_out[:res.shape[0]]
-        dst.copy_(res, non_blocking=True)             # device -> pinned host buffer (a pageable .cpu() copy runs at a fraction of PCIe)
+        res = img if rank == 0 else None
+        if res is not None:
+            dst = pinned_out[:res.shape[0]]
+            dst.copy_(res, non_blocking=True)
         main.synchronize()
-        return dst
+        return res
 
     def timed(fn, steps, profile=False):
         evs = []
@@ -479,6 +539,45 @@ def run_b200(args):
     L.aninerf_profile_read(ms_buf, calls_buf, 1)
     stage_ms = {name: (ms_buf[i] / max(1, calls_buf[i])) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
     e2e_ms = timed(lambda: step_e2e(), args.steps)
+    # a longer run of the same step (the K timed steps last tens of milliseconds, at N = 8 ~10 ms: one disturbance moves them by %)
+    long_frames = 200
+    long_ms = timed(lambda: step_device(), long_frames)
+    # ---- the FULL contract (the package's default mode and what the reference / the CPU arm evaluate): posed + canonical
+    # blend-weight field + NeRF, dense raw, pbw / tbw rows -- device-timed, and end to end through Renderer.render(batch) --------
+    full_contract = None
+    if world == 1:
+        cfg_full = config.make_cfg(perturb=0.)
+        r_full = Renderer(net, cfg_full)
+        host_full = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in full.items()}
+        h2d_full = sum(v.numel() * v.element_size() for v in host_full.values() if torch.is_tensor(v))
+
+        def full_device():
+            o = r_full.render_device(full, want_bw=True)
+            return o, r_full.select_rows(o)
+
+        def full_e2e():
+            return r_full.render(r_full.to_device(host_full, dev))
+
+        for _ in range(2):
+            full_device()
+            res = full_e2e()
+        d2h_full = sum(v.numel() * v.element_size() for v in res.values())
+        L.aninerf_profile_read(ms_buf, calls_buf, 1)
+        fc_launch0 = L.aninerf_launch_count()
+        fc_dev_ms = timed(lambda: full_device(), args.steps, profile=True) / args.steps
+        fc_launches = (L.aninerf_launch_count() - fc_launch0) / args.steps
+        L.aninerf_profile_read(ms_buf, calls_buf, 1)
+        fc_stage = {name: (ms_buf[i] / max(1, calls_buf[i])) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
+        fc_e2e_ms = timed(lambda: full_e2e(), args.steps) / args.steps
+        full_contract = {
+            'mode': 'full contract = config.b200_render_only False (default): rgb/acc/depth + raw (1,R*64,4) + pbw/tbw rows, as the reference returns them',
+            'value': n_rays * S / (fc_dev_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': fc_dev_ms, 'stage_ms': fc_stage,
+            'gpu_launches_per_step': fc_launches,
+            'algorithmic_tflops': n_active * (2 * FLOP_BW + FLOP_NERF) / (fc_dev_ms * 1e-3) / 1e12,
+            'e2e': {'call': 'Renderer.render(Renderer.to_device(pinned host batch)) -> host dict', 'value': n_rays * S / (fc_e2e_ms * 1e-3), 'unit': 'samples/s',
+                    'ms_per_step': fc_e2e_ms, 'h2d_bytes_per_step': int(h2d_full), 'd2h_bytes_per_step': int(d2h_full)},
+        }
+        del res, r_full, host_full
     clk = clocks.stop() if rank == 0 else None
 
     samples = n_rays * S
@@ -515,8 +614,12 @@ def run_b200(args):
                               if peer is not None else 'NCCL all_gather + reorder'),
                    'weights': 'random init, seed 0, reference checkpoint layout'},
         'e2e': {'value': samples / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
-                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int((n_rays if rank == 0 else my_rays) * 20)},
+                'call': ('Renderer.render(Renderer.to_device(pinned host batch)) -> host maps' if world == 1 else
+                         'per rank: to_device(its rays) + PeerVolume.upload(1/N of pbw, NVLink push) + render_device(peers=...) + barrier; rank 0 downloads the image'),
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(n_rays * 20)},
         'gpu_launches': int(launches),
+        'long_run': {'frames': long_frames, 'ms_per_frame': long_ms / long_frames, 'samples_per_s': samples / (long_ms / long_frames * 1e-3)},
+        'full_contract': full_contract,
         'clocks': clk,
         'roofline': roofline,
         'stage_ms_rank0': stage_ms,
@@ -538,8 +641,19 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, sec, n = cpu_render_rate(frame, cam, sd, args.size, reps=3)
         line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                'mode': 'full contract (the reference has no render-only mode): compare with `full_contract`',
                                 'sample': f'oracle/ port of Renderer.render, {CPU_SAMPLE_RAYS} rays x 64 samples of the same frame, '
                                           f'torch {torch.__version__} CPU, median of 3 ({sec:.2f} s each)'}
+        try:
+            del flush
+            torch.cuda.empty_cache()
+            erate, ems, erays = eager_cuda_rate(frame, cam, sd, args.size, dev)
+            line['other_baselines'] = {'reference_eager_cuda': {
+                'value': erate, 'unit': 'samples/s', 'ms_per_frame': ems, 'rays': erays, 'mode': 'full contract',
+                'what': 'the reference algorithm as its users run it on a GPU: eager PyTorch (torch ' + torch.__version__ + ') on CUDA tensors, fp32 '
+                        '(TF32 off), 2048-ray chunks, boolean-mask indexing, per-frame .cpu() of the outputs -- oracle/ restatement on the device, whole frame, CUDA events'}}
+        except Exception as e:  # noqa: BLE001
+            line['other_baselines'] = {'reference_eager_cuda': {'error': repr(e)}}
     if not args.no_extra:
         try:
             extra = other_configs(dev, frame, rank, world)
