@@ -33,7 +33,7 @@ int bw_forward_impl(aninerf_net *net, int field, int latent_index, const int64_t
                     float *tpts_out, int precision, cudaStream_t st);
 int nerf_forward_impl(aninerf_net *net, int latent_index, const int64_t *latent_dev, const float *pts, const float *viewdir, int64_t n, const int32_t *n_dev,
                       float *sigma_out, float *rgb_out, const float *dists, const float *tbounds, const int32_t *index, float *raw_out,
-                      float *sigma_masked_out, int precision, cudaStream_t st);
+                      float *sigma_masked_out, int precision, cudaStream_t st, int density_only);
 
 // ---- optional per-stage timing (CUDA events on the launching stream) ---------------------------
 enum { ST_SPLIT = 0, ST_CLEAR, ST_MASK, ST_SCAN, ST_COMPACT, ST_BW_POSE, ST_BW_CANON, ST_NERF, ST_COMPOSITE, ST_COUNT };
@@ -234,7 +234,7 @@ static int render_rays_impl(aninerf_net *net, const aninerf_frame *fr, const ani
   {
     StageTimer t(ST_NERF, st);
     if ((rc = nerf_forward_impl(net, nerf_latent, fr->latent_index_dev, s.tpts, s.viewdir, n, out->n_active, nullptr, nullptr, s.dists, fr->tbounds,
-                                dense ? index : nullptr, dense ? out->raw : s.raw_c, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st)))
+                                dense ? index : nullptr, dense ? out->raw : s.raw_c, pr->want_bw ? out->sigma_masked : nullptr, pr->nerf_precision == 3 ? 3 : 1, st, 0)))
       return rc;
   }
   // 5. compositing
@@ -364,9 +364,9 @@ int aninerf_query_alpha(aninerf_net *net, const aninerf_frame *fr, const float *
   if ((rc = bw_forward_impl(net, bw_field, bw_latent, bw_lat_dev, ppts, nullptr, w24, fr->pbw_dims, fr->pbounds, n, n_active, fr->A, nullptr, tpts,
                             bw_precision == 1 ? 1 : 3, st)))
     return rc;
-  // density only: the colour head is evaluated but discarded (viewdir = the canonical points, any finite input works)
+  // density only (TPoseHuman.calculate_alpha, tpose_nerf_network.py:241-250): the kernel stops after the trunk + alpha_fc
   if ((rc = nerf_forward_impl(net, fr->latent_index_dev ? 0 : fr->latent_index, fr->latent_index_dev, tpts, tpts, n, n_active, sigma, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1,
-                              st)))
+                              st, 1)))
     return rc;
   ANI_CUDA(cudaMemsetAsync(sigma_out, 0, n * 4, st));
   return launch_scatter_scalar(sigma, index, n_active, n, sigma_out, st);

@@ -21,6 +21,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// arrive on a barrier in ANOTHER CTA of the cluster with the default (.release.cta) semantics.  `.release.cluster` compiles to
+// MEMBAR.ALL.CTA + MEMBAR.ALL.GPU in front of the arrive (hundreds of cycles per call); the data these barriers guard is shared
+// memory written before a fence.proxy.async (itself a MEMBAR.ALL.CTA) and read by the tensor core, so CTA scope is what is needed
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -155,6 +161,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B (64 bf16 along K), 8-row groups of 1024 B (= sbo), the 16-byte
+// chunk c of row r stored at chunk position c ^ (r % 8); the K=16 slice j of the 64-wide block starts 32*j bytes into the row.
+// The block base must be 1024-byte aligned.  (tools/bench_mma.cu checks this layout numerically and measures it: 129.7 cycles per
+// M=256 N=256 K=16 MMA against 152.1 for the SWIZZLE_NONE core-matrix layout; floor 128.)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of the 16-byte chunk `c` (8 K elements) of row `row` inside a SWIZZLE_128B K-block
+__host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int c) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((c ^ row) & 7) << 4));
 }
 // instruction descriptor: D=f32, A=B=bf16, both K-major
 __device__ __forceinline__ uint32_t instr_desc(int n, int m) {

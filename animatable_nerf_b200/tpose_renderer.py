@@ -159,10 +159,10 @@ class Renderer:
         return host
 
     def render(self, batch):
-        """Renderer.render (tpose_renderer.py:159-186).  No gradient required: CPU tensors (:154-155).  Gradient enabled on a
-        training-mode network: device tensors that carry the autograd graph to the Network parameters (the contract
-        tpose_trainer.NetworkWrapper relies on, lib/train/trainers/tpose_trainer.py:28)."""
-        if torch.is_grad_enabled() and self.net.training and any(p.requires_grad for p in self.net.parameters()):
+        """Renderer.render (tpose_renderer.py:159-186).  No gradient attached (evaluation runs under torch.no_grad(), run.py:62):
+        CPU tensors (:154-155).  Gradient mode with trainable parameters: device tensors that carry the autograd graph to the
+        Network parameters (the contract tpose_trainer.NetworkWrapper relies on, lib/train/trainers/tpose_trainer.py:28)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters()):      # = `rgb_map.requires_grad` of tpose_renderer.py:154
             from .tpose_trainer import render_with_grad
             return render_with_grad(self, batch)
         with torch.no_grad():

@@ -385,6 +385,7 @@ def other_configs(dev, frame, rank, world):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+@torch.no_grad()
 def run_b200(args):
     import torch.distributed as dist
     from animatable_nerf_b200 import _lib, config, frontend, ray_tiles, synthetic

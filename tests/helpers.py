@@ -55,7 +55,8 @@ def check_selected_rows(renderer, dv, dbg, bw_tol=1e-5, eps=SIGMA_EPS):
         forced arg-max of a chunk whose best and runner-up sigma differ by less than `eps` on the oracle side;
       * on the rows both sides select, pbw and tbw agree within `bw_tol`.
     dv: render_device(want_bw=True) result; dbg: the oracle's _debug (needs alpha_ind, sigma_masked, chunk_active).
-    Returns (n_common, n_mismatch)."""
+    Returns (gpu rows, mask of those the oracle selects too, oracle rows, mask of those the GPU selects too, packed pbw, packed tbw,
+    number of one-sided rows, number of oracle rows with |sigma| <= eps -- the population the one-sided rows can come from)."""
     n_active = int(dv['n_active'].item())
     sel, n_sel = renderer.select_rows(dv)
     sel = sel[:n_active].bool().cpu()
@@ -80,4 +81,5 @@ def check_selected_rows(renderer, dv, dbg, bw_tol=1e-5, eps=SIGMA_EPS):
     common_in_gpu = both[rows]                                   # which of the GPU's packed rows the oracle selected too
     ref_rows = want.nonzero().reshape(-1)
     common_in_ref = both[ref_rows]
-    return rows, common_in_gpu, ref_rows, common_in_ref, pbw.cpu(), tbw.cpu(), int(mism.numel())
+    n_near = int((sig.abs() <= eps).sum()) + int(dbg['chunk_active'].numel())
+    return rows, common_in_gpu, ref_rows, common_in_ref, pbw.cpu(), tbw.cpu(), int(mism.numel()), n_near

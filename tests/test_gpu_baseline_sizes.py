@@ -22,6 +22,13 @@ def dev():
     assert torch.cuda.is_available(), 'these tests need the B200'
     return torch.device('cuda:0')
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Evaluation runs under torch.no_grad() (run.py:62 of the reference); with gradients enabled Renderer.render returns device
+    tensors carrying the graph (tests/test_gpu_train.py covers that mode)."""
+    with torch.no_grad():
+        yield
+
 
 def _renderer(dev, sd, **over):
     from animatable_nerf_b200 import config
@@ -78,9 +85,9 @@ def test_config2_whole_frame_full_contract_vs_oracle(dev, frame_c2):
     print('config 2 whole frame:', n, 'rays', n_active, 'active; max abs error', err, 'raw', raw_err)
     assert max(err.values()) <= RGB_TOL and raw_err <= RGB_TOL
     # canonical points <= 1e-5 is implied by tbw <= 1e-5 on every common row below (tbw is sampled at those points)
-    rows, cg, ref_rows, cr, pbw, tbw, n_mism = check_selected_rows(r, dv, dbg)
-    print('selected rows', rows.numel(), 'oracle', ref_rows.numel(), 'one-sided', n_mism)
-    assert n_mism <= 1e-3 * ref_rows.numel() + 8
+    rows, cg, ref_rows, cr, pbw, tbw, n_mism, n_near = check_selected_rows(r, dv, dbg)
+    print('selected rows', rows.numel(), 'oracle', ref_rows.numel(), 'one-sided', n_mism, 'of', n_near, 'oracle rows within the sigma noise of the threshold')
+    assert n_mism <= n_near
     assert float((pbw[cg] - ref['pbw'][0][cr]).abs().max()) <= BW_TOL
     assert float((tbw[cg] - ref['tbw'][0][cr]).abs().max()) <= BW_TOL
     # render-only (the mode the headline times): same maps from the compact rows

@@ -17,6 +17,13 @@ def dev():
     assert torch.cuda.is_available(), 'these tests need the B200'
     return torch.device('cuda:0')
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Evaluation runs under torch.no_grad() (run.py:62 of the reference); with gradients enabled Renderer.render returns device
+    tensors carrying the graph (tests/test_gpu_train.py covers that mode)."""
+    with torch.no_grad():
+        yield
+
 
 def _renderer(dev, sd, **over):
     from animatable_nerf_b200 import config
@@ -77,8 +84,8 @@ def test_render_internals_vs_oracle(dev):
         assert float(margin) <= 1e-5, f'outside mismatch at row {i} with margin {float(margin)}'
     # the pbw / tbw rows of the contract: row SET vs the oracle (mismatches only within the sigma noise of the threshold /
     # of the chunk maximum), values on the common rows within 1e-5 -- unconditionally
-    rows, cg, ref_rows, cr, pbw, tbw, n_mism = check_selected_rows(r, dv, dbg)
-    assert n_mism <= 8
+    rows, cg, ref_rows, cr, pbw, tbw, n_mism, n_near = check_selected_rows(r, dv, dbg)
+    assert n_mism <= n_near
     assert float((pbw[cg] - ref['pbw'][0][cr]).abs().max()) <= BW_TOL
     assert float((tbw[cg] - ref['tbw'][0][cr]).abs().max()) <= BW_TOL
     # full contract through render(): the same rows, on the host

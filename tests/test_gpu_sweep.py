@@ -15,6 +15,13 @@ def dev():
     assert torch.cuda.is_available(), 'these tests need the B200'
     return torch.device('cuda:0')
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Evaluation runs under torch.no_grad() (run.py:62 of the reference); with gradients enabled Renderer.render returns device
+    tensors carrying the graph (tests/test_gpu_train.py covers that mode)."""
+    with torch.no_grad():
+        yield
+
 
 def _net(dev, sd):
     from animatable_nerf_b200 import config

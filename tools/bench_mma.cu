@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define CK(x)                                                                       \
   do {                                                                              \
@@ -350,6 +351,160 @@ __global__ void __launch_bounds__(320, 1) handoff_kernel(int n_sts, Result *res)
   }
 }
 
+// ---- correctness of the SWIZZLE_128B K-major layout used by csrc/mlp_tcgen05.cu: D[256 x N] = A[256 x K] * B[N x K]^T with
+// cta_group::2 (CTA r holds A rows [128r, 128r+128) and B rows [N/2 r, N/2 (r+1))), K = 64 * kblocks, operands written in the
+// layout the kernel's epilogue / weight packer use:
+//   element (row, k) of a K-block (64 wide) at  (row/8)*1024 + (row%8)*128 + (((k/8) ^ (row%8)) * 16) + (k%8)*2
+__device__ __forceinline__ uint32_t sw128_off(int row, int k) {   // byte offset inside one K-block of `rows` rows
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+__global__ void __launch_bounds__(320, 1) verify_kernel(const uint16_t *A, const uint16_t *B, int n, int kblocks, float *D, int *status, int ts) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *sA = smem;                          // kblocks x 16 KB
+  uint8_t *sB = smem + 4 * 16384;              // kblocks x (n/2 rows x 128 B)
+  __shared__ uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int K = 64 * kblocks, nb = n / 2;
+  for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+    const int row = i / K, k = i % K;
+    *reinterpret_cast<uint16_t *>(sA + (k >> 6) * 16384 + sw128_off(row, k & 63)) = A[(size_t)(rank * 128 + row) * K + k];
+  }
+  for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+    const int row = i / K, k = i % K;
+    *reinterpret_cast<uint16_t *>(sB + (k >> 6) * (nb * 128) + sw128_off(row, k & 63)) = B[(size_t)(rank * nb + row) * K + k];
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc<2>(smem_u32(&tmem_slot), 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (ts && warp < 4) {
+    // A operand in tensor memory: lane = row, 32-bit column c of the operand = K elements (2c, 2c+1), element 2c in the low half
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t v[16];
+      for (int j = 0; j < 16; ++j) {
+        const int k = 2 * (c0 + j);
+        v[j] = (uint32_t)A[(size_t)(rank * 128 + row) * K + k] | ((uint32_t)A[(size_t)(rank * 128 + row) * K + k + 1] << 16);
+      }
+      tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 8 && lane == 0) {
+    bool ok = true;
+    if (rank == 0) {
+      const uint32_t idesc = instr_desc(n, 256);
+      for (int i = 0; i < 4 * kblocks; ++i) {
+        const uint64_t ad = desc_sw128(smem_u32(sA) + (i >> 2) * 16384 + (i & 3) * 32);
+        const uint64_t bd = desc_sw128(smem_u32(sB) + (i >> 2) * (nb * 128) + (i & 3) * 32);
+        if (ts) umma_ts<2>(tmem, tmem + 256 + i * 8, bd, idesc, i ? 1u : 0u);
+        else umma_ss<2>(tmem, ad, bd, idesc, i ? 1u : 0u);
+      }
+      umma_commit<2>(smem_u32(&bars[0]));
+    }
+    ok = mbar_wait(smem_u32(&bars[0]), 0);
+    if (!ok) atomicExch(status, 1);
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 4) {
+    for (int c = 0; c < n; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) D[(size_t)(rank * 128 + warp * 32 + lane) * n + c + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem, 512);
+  }
+}
+
+static uint16_t f2bf_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float bf2f_host(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+static void run_verify() {
+  printf("## 0. SWIZZLE_128B K-major operand layout: numerical check of D = A B^T (cta_group::2, M = 256)\n");
+  for (int ts = 0; ts < 2; ++ts)
+  for (int n : {256, 128, 32})
+    for (int kblocks : {1, 4}) {
+      const int K = 64 * kblocks;
+      uint16_t *hA = (uint16_t *)malloc(256 * K * 2), *hB = (uint16_t *)malloc(n * K * 2);
+      uint32_t seed = 12345u + n + kblocks;
+      auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xffff) / 65536.0f - 0.5f; };
+      for (int i = 0; i < 256 * K; ++i) hA[i] = f2bf_host(rnd());
+      for (int i = 0; i < n * K; ++i) hB[i] = f2bf_host(rnd());
+      uint16_t *dA, *dB;
+      float *dD;
+      int *dS;
+      CK(cudaMalloc(&dA, 256 * K * 2));
+      CK(cudaMalloc(&dB, n * K * 2));
+      CK(cudaMalloc(&dD, 256 * n * 4));
+      CK(cudaMalloc(&dS, 4));
+      CK(cudaMemcpy(dA, hA, 256 * K * 2, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dB, hB, n * K * 2, cudaMemcpyHostToDevice));
+      CK(cudaMemset(dD, 0xff, 256 * n * 4));
+      CK(cudaMemset(dS, 0, 4));
+      const int smem = 8 * 16384;
+      CK(cudaFuncSetAttribute(verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2);
+      cfg.blockDim = dim3(320);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, verify_kernel, (const uint16_t *)dA, (const uint16_t *)dB, n, kblocks, dD, dS, ts));
+      CK(cudaDeviceSynchronize());
+      float *hD = (float *)malloc(256 * n * 4);
+      int st = 0;
+      CK(cudaMemcpy(hD, dD, 256 * n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+      double worst = 0;
+      for (int m = 0; m < 256; ++m)
+        for (int j = 0; j < n; ++j) {
+          double acc = 0;
+          for (int k = 0; k < K; ++k) acc += (double)bf2f_host(hA[m * K + k]) * (double)bf2f_host(hB[j * K + k]);
+          const double e = fabs(acc - (double)hD[m * n + j]);
+          worst = e > worst ? e : worst;
+        }
+      printf("%s N=%3d K=%3d: max |D - A B^T| = %.3e %s%s\n", ts ? "A in TMEM (.ts, packed pairs, K even in the low half)" : "A in smem  (SWIZZLE_128B)", n, K, worst, worst < 1e-4 ? "OK" : "MISMATCH", st ? " (TIMEOUT)" : "");
+      free(hA); free(hB); free(hD);
+      cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
+    }
+}
+
 template <int PAIR>
 static void run_mma(const char *name, int src, int n, int n_mma, int side, int side_warps, int clusters, Result *d_res) {
   const int smem = A_BYTES + B_BYTES + 65536;
@@ -391,6 +546,11 @@ int main(int argc, char **argv) {
   cudaDeviceProp p;
   CK(cudaGetDeviceProperties(&p, 0));
   printf("# %s, %d SMs, %d cluster(s) of 2 CTAs\n", p.name, p.multiProcessorCount, clusters);
+  if (argc > 2 && !strcmp(argv[2], "verify")) {
+    run_verify();
+    return 0;
+  }
+  run_verify();
   const int NM = 256;
   const char *srcs[3] = {"A smem SWIZZLE_NONE", "A smem SWIZZLE_128B", "A in TMEM (.ts)"};
   printf("## 1. MMA rate, nothing else running (aux = cycles to ISSUE the %d MMAs)\n", NM);

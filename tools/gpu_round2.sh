@@ -15,6 +15,8 @@ benchq)
   timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --no-extra > gpurun_out/benchq_$tag.json 2> gpurun_out/benchq_$tag.err; echo "benchq rc=$?"; cut -c1-2500 gpurun_out/benchq_$tag.json; tail -5 gpurun_out/benchq_$tag.err;;
 ref)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/ref_$tag.json 2> gpurun_out/ref_$tag.err; echo "ref rc=$?"; cut -c1-800 gpurun_out/ref_$tag.json;;
+verify)
+  timeout 120 tools/bench_mma 1 verify > gpurun_out/verify_$tag.log 2>&1; echo "verify rc=$?"; cat gpurun_out/verify_$tag.log;;
 mma)
   timeout 120 tools/bench_mma 1 > gpurun_out/mma1_$tag.log 2>&1; echo "mma1 rc=$?"; cat gpurun_out/mma1_$tag.log
   timeout 120 tools/bench_mma 74 > gpurun_out/mma74_$tag.log 2>&1; echo "mma74 rc=$?"; grep -v "^#" gpurun_out/mma74_$tag.log | head -40;;
