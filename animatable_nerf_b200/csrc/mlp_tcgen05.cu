@@ -2,22 +2,29 @@
 // :304-315) and the canonical NeRF MLP (tpose_nerf_network.py:252-275) -- as ONE persistent,
 // warp-specialised tcgen05 kernel family for sm_100a.
 //
-// Work unit: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2, M = 256).  Each CTA owns 128 samples: their bf16 A operand
-// lives in its shared memory (K-major SWIZZLE_128B blocks of 64 K elements: 128 rows x 128 B) and their fp32 accumulator in
-// its TMEM (128 lanes x 256 columns, two buffers alternating by layer).  Weights stream from L2 through a ring of 16 KB
-// stages filled by bulk TMA copies (cp.async.bulk) of pre-packed SWIZZLE_128B operand blocks; each CTA of the pair loads
-// HALF of every block (the M=256 MMA reads B from both CTAs), which halves the L2 -> SM weight traffic per sample.  One
-// elected thread of the leader CTA issues tcgen05.mma (M=256, N<=256, K=16); eight epilogue warps per CTA (two threads per
-// row, each owning half of every 64-column quarter) read the accumulator back with tcgen05.ld, apply bias+ReLU, re-quantise
-// to bf16 (hi, and lo for the split-precision mode) and write the next layer's A operand in place.  Positional encoding is
-// generated in-kernel straight into the A operand; the last epilogue is the field's head (softmax + inverse LBS, or
-// alpha/rgb activation + tbounds masking + scatter).
+// Work unit: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2, M = 256).  Each CTA owns 128 samples; their fp32 accumulator lives
+// in its TMEM (128 lanes x 256 columns, two buffers alternating by layer).  THE HIDDEN ACTIVATIONS NEVER LEAVE TENSOR MEMORY: the
+// epilogue of layer l reads its accumulator buffer with tcgen05.ld, applies bias + ReLU, re-quantises to bf16 (hi, and lo for the
+// split-precision mode) and writes the packed pairs with tcgen05.st IN PLACE over the columns it has just read -- a retired
+// accumulator buffer is exactly big enough for the next layer's A operand (x1: 128 of its 256 columns, x3: all of them) -- and
+// layer l+1 is issued in the .ts form (A from tensor memory, `tcgen05.mma [d], [a], b_desc`), accumulating into the OTHER
+// buffer.  Only the 64-wide input encodings (PE(xyz), PE(viewdir)) are shared-memory operands (K-major SWIZZLE_128B blocks).
+// Weights stream from L2 through a ring of 32 KB stages filled by bulk TMA copies (cp.async.bulk) of pre-packed
+// SWIZZLE_128B blocks; each CTA of the pair loads HALF of every block (the M=256 MMA reads B from both CTAs), which halves the
+// L2 -> SM weight traffic per sample.  One thread of the leader CTA issues tcgen05.mma (M=256, N<=256, K=16); eight
+// epilogue warps per CTA (two threads per row, each owning half of every 64-column quarter).  Positional encoding is generated
+// in-kernel straight into the A operand; the last epilogue is the field's head (softmax + inverse LBS, or alpha/rgb activation
+// + tbounds masking + scatter).
 //
-// Pipelining (QP, "quarter pipelining"): the epilogue of layer l publishes the next layer's A operand one 64-column K-block at a
-// time (a_ready[q]) and the accumulator alternates between two TMEM buffers, so the MMAs of layer l+1 start as soon as the first
-// quarter is written and run while the epilogue produces the other three.  Every layer is issued as full-width N = 256 MMAs:
-// tools/bench_mma.cu measured that an MMA never retires faster than ~105 cycles whatever its N, so the N = 128 halves of the
-// round-1 kernel cost 2 x 105..131 cycles where one N = 256 MMA costs 129.5 (the floor is 128).
+// Why: tools/bench_mma.cu (profiles/r02_mma_microbench.md).  (1) An M=256 N=256 K=16 MMA takes 152 cycles with both operands in the
+// SWIZZLE_NONE core-matrix layout of round 1, 129.7 with SWIZZLE_128B, 128.3 with A in tensor memory (floor 128).  (2) No MMA
+// retires faster than ~105 cycles whatever its N, so the N = 128 halves of round 1 cost 2 x 105..131 cycles per K=16 slice.
+// (3) The ONE thread that issues the MMAs is the scarcest resource of the kernel: every dependent scalar instruction, mbarrier
+// try_wait (~100 cycles even when complete) and commit between two MMAs is tensor-pipe idle time once it exceeds the MMA time.
+//
+// Pipelining (QP, "quarter pipelining"): the epilogue publishes the next layer's operand one 64-column K-block at a time
+// (a_ready[q]), so the MMAs of layer l+1 start as soon as the first quarter is written and run while the epilogue produces the
+// other three.
 //
 // Precision modes: NPASS=1 single bf16 product; NPASS=3 "bf16x3": x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // with fp32 accumulation (fp32-equivalent; the blend-weight field needs it for the 1e-5 gate).
@@ -37,11 +44,11 @@ namespace aninerf {
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_M = 128;
 constexpr int KB_BYTES = TILE_M * 128;       // one K-block of the A tile: 128 rows x 64 bf16 (SWIZZLE_128B), 16 KB
-constexpr int PE_CHUNK0 = 0;                 // A chunks (8 K elements each) 0..7 : K-block 0 = PE(xyz) 63 + pad
-constexpr int HID_CHUNK0 = 8;                // A chunks 8..39 : K-blocks 1..4 = hidden 256
-constexpr int VIEW_CHUNK0 = 40;              // A chunks 40..47: K-block 5 = PE(viewdir) 27 + pad (single-pass NeRF field only; the
-                                             // split-precision one has no room and reuses K-block 0 once layer 5 has run)
-constexpr int STAGE_BYTES = 16384;
+constexpr int PE_CHUNK0 = 0;                 // shared-memory A block 0 (chunks of 8 K elements 0..7): PE(xyz) 63 + pad
+constexpr int VIEW_CHUNK0 = 8;               // shared-memory A block 1 (chunks 8..15): PE(viewdir) 27 + pad (NeRF field)
+constexpr int KB_PE = 0, KB_HID0 = 1, KB_VIEW = 5;   // Step::a_kb: 0 PE(xyz) block, 1..4 hidden quarters (tensor memory), 5 PE(viewdir) block
+constexpr int STAGE_BYTES = 32768;          // ring stage: two K-blocks of a 256-wide layer (x1), or the hi + lo block of one (x3): the single
+                                             // MMA-issuing thread spends ~350 cycles per stage on waits / commits / decode whatever the stage holds
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_STEPS = 68;
 constexpr int SMEM_LIMIT = 232448;           // 227 KB
@@ -102,6 +109,8 @@ struct MlpArgs {
   const int32_t *index;
   float *raw_out;
   float *sigma_masked_out;
+  int32_t debug;               // bring-up (ANINERF_DEBUG_MLP, timing experiments only -- results are garbage): 1 = the producer signals `full`
+                               // without copying (no weight traffic); 2 = the epilogue skips its tensor-memory stores
   int32_t density_only;        // NeRF field: stop after the trunk (TPoseHuman.calculate_alpha, tpose_nerf_network.py:241-250): sigma_out only
   unsigned long long *trace;   // bring-up: clock64 timeline of one unit tile of block 0 (null = off)
   int32_t trace_iter;          // which of block 0's tiles is traced (0 = first); slots 160+i: start of its i-th tile
@@ -111,7 +120,7 @@ struct MlpArgs {
 // (arrived); +4 MMA waits a_ready, +5 MMA woke, +6 MMA issued the layer
 #define ANI_TRACE(slot)                                                              \
   do {                                                                               \
-    if (tracing) args.trace[(slot)] = (unsigned long long)clock64();                 \
+    if (tracing) trace_base[(slot)] = (unsigned long long)clock64();                 \
   } while (0)
 
 // write 8 consecutive K elements of `row` (one 16-byte chunk) into A chunk `chunk` (K-block chunk / 8, SWIZZLE_128B);
@@ -226,26 +235,27 @@ constexpr int PROD_LANES = 8;                      // producer lanes take turns 
 
 template <int NPASS, bool NERF>
 struct Cfg {
-  static constexpr bool VIEW_SEP = NERF && NPASS == 1;           // PE(viewdir) in its own K-block: the next tile's PE(xyz) can be prefetched
-  static constexpr int A_KB = 5 + (VIEW_SEP ? 1 : 0);
-  static constexpr int A_PLANE = A_KB * KB_BYTES;                // 80 / 96 KB per hi / lo plane
+  static constexpr int A_KB = NERF ? 2 : 1;                       // shared-memory operand blocks: PE(xyz) [, PE(viewdir)]
+  static constexpr int A_PLANE = A_KB * KB_BYTES;                 // per hi / lo plane
   static constexpr int A_TOTAL = A_PLANE * (NPASS == 3 ? 2 : 1);
+  static constexpr int SCR_BYTES = NERF ? 0 : TILE_M * 16 * 4;    // blend-weight head: exchange between the row's two threads
   static constexpr int HEAD_BYTES = NERF ? 2576 : 1152;
   static constexpr int XCHG = NERF ? XCHG_BYTES : 0;             // the blend-weight head exchanges through the dead A operand
   static constexpr int STEP_BYTES = MAX_STEPS * (int)sizeof(Step);
   // (one layer's bias at a time, staged by the row threads in the idle window before the layer's accumulator is ready: with the
   // whole 9 KB table resident the split-precision blend-weight field would have three ring stages instead of four)
   static constexpr int BIAS_BYTES = 256 * 4;
-  static constexpr int FIXED = A_TOTAL + HEAD_BYTES + XCHG + STEP_BYTES + BIAS_BYTES + 256;
+  static constexpr int FIXED = A_TOTAL + SCR_BYTES + HEAD_BYTES + XCHG + STEP_BYTES + BIAS_BYTES + 256;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
   static_assert(STAGES >= 2, "weight ring needs at least two stages");
   static constexpr int TMEM_COLS = 512;                         // two accumulators, alternating by layer
   // offsets (A planes and the ring first: SWIZZLE_128B blocks need 1024-byte alignment)
   static constexpr int OFF_A_HI = 0;
   static constexpr int OFF_A_LO = A_PLANE;                      // only when NPASS == 3
   static constexpr int OFF_RING = A_TOTAL;
-  static constexpr int OFF_HEAD = OFF_RING + STAGES * STAGE_BYTES;
+  static constexpr int OFF_SCR = OFF_RING + STAGES * STAGE_BYTES;
+  static constexpr int OFF_HEAD = OFF_SCR + SCR_BYTES;
   static constexpr int OFF_XCHG = OFF_HEAD + HEAD_BYTES;
   static constexpr int OFF_STEPS = OFF_XCHG + XCHG;
   static constexpr int OFF_BIAS = OFF_STEPS + STEP_BYTES;
@@ -274,12 +284,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + 4);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 5);
   static_assert((2 * C::STAGES + 6) * 8 <= 216, "barrier block overflow");
-  // XT: cross-tile prefetch.  The next tile's input encoding is written into K-block 0 right after the LAST layer's accumulator
-  // barrier (K-block 0 is dead since layer 5), so the MMA issuer rolls from the last layer straight into the next tile's layer 0
-  // while the epilogue warps are still busy with this tile's head.  Not for the split-precision NeRF field: its PE(viewdir) lives
-  // in K-block 0 and is read by the last layer.
-  constexpr bool XT = !NERF || C::VIEW_SEP;
-  constexpr int VCHUNK0 = C::VIEW_SEP ? VIEW_CHUNK0 : PE_CHUNK0;
+  // XT: cross-tile prefetch.  The next tile's input encoding is written into the PE(xyz) block right after the LAST layer's
+  // accumulator barrier (the block is dead since layer 5), so the MMA issuer rolls from the last layer straight into the next
+  // tile's layer 0 while the epilogue warps are still busy with this tile's head.
+  constexpr bool XT = true;
+  constexpr int VCHUNK0 = VIEW_CHUNK0;
   float *s_grid = reinterpret_cast<float *>(smem + C::OFF_BAR + 224);   // lo[3], (dim-1)/ext [3] of the SMPL-weight volume
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,8 +343,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               const Step ps = s_steps[s];
               const uint32_t bytes = (uint32_t)(F.layers[l].n_pad / PAIR) * 128u * ps.n_kb *
                                      (((ps.flags & STEP_HI) ? 1u : 0u) + ((ps.flags & STEP_LO) ? 1u : 0u));   // this CTA's half of the stage
-              mbar_expect_tx(bar_full + 8 * stage, bytes);
-              bulk_g2s(smem_u32(ring + stage * STAGE_BYTES), F.image + ps.w_off + cta_rank * bytes, bytes, bar_full + 8 * stage);
+              if (args.debug & 1) {
+                mbar_arrive(bar_full + 8 * stage);
+              } else {
+                mbar_expect_tx(bar_full + 8 * stage, bytes);
+                bulk_g2s(smem_u32(ring + stage * STAGE_BYTES), F.image + ps.w_off + cta_rank * bytes, bytes, bar_full + 8 * stage);
+              }
             }
             __syncwarp((1u << PROD_LANES) - 1u);
             turn = (turn + 1) % PROD_LANES;
@@ -349,48 +362,78 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     }
   } else if (warp > RW) {
     const int role = warp - (RW + 1);
-    if (leader && role == 0) {
-      // ===== MMA issuer (leader CTA) ===============================================================
-      uint32_t g = 0, a_phase = 0, lc = 0;                          // g: ring position; lc: running layer count (accumulator buffer)
+    if (leader && role == 0 && lane == 0) {
+      // ===== MMA issuer (leader CTA): ONE thread.  Everything it does between two MMAs is on the critical path of the tensor pipe
+      // (tools/bench_mma.cu: a few dozen dependent scalar instructions per MMA already halve the rate), so the loop is kept to:
+      // per ring stage one decode + one `full` wait + one commit; per K-block one descriptor per operand and (first touch of a
+      // quarter) one a_ready wait; per K=16 slice a constant +32 bytes / +8 columns. ====================================
+      uint32_t stage = 0, full_phase = 0, a_phase = 0, lc = 0;      // ring position; lc: running layer count (accumulator buffer)
       const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI), a_lo = smem_u32(smem + C::OFF_A_LO);
+      const uint32_t ring_u32 = smem_u32(ring);
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-        const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && lane == 0;
+        const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units;
+        unsigned long long *const trace_base = args.trace;
         for (int l = 0; l < n_layers; ++l, ++lc) {
           const int n_pad = F.layers[l].n_pad;
           const int s0 = F.layers[l].step0, n_layer_steps = F.layers[l].n_steps;
           const uint32_t idesc = instr_desc(n_pad, TILE_M * PAIR);
           const uint32_t acc = tmem_base + (lc & 1u) * 256u;
+          const uint32_t a_prev = tmem_base + ((lc & 1u) ^ 1u) * 256u;      // the previous layer's buffer: this layer's hidden operand
+          const uint32_t blk = (uint32_t)(n_pad / PAIR) * 128u;             // one K-block of this CTA's weight rows, one plane
           ANI_TRACE(8 + 16 * l + 4);
-          // K-block q of the hidden operand (and, at layer 0, the input encoding) is ready once a_ready[q] completes; the
-          // accumulator buffer was drained two layers ago (the epilogue threads are one layer behind at most)
+          // K-block q of the hidden operand is ready once a_ready[q] completes.  Layer 0 reads the input encoding only: its four
+          // barriers complete together and are all consumed up front (never after the commit: the epilogue's arrivals for layer 1
+          // must not overtake).  The accumulator buffer was drained two layers ago.
           int next_q = 0;
-          for (int s = s0; s < s0 + n_layer_steps; ++s, ++g) {
+          if (l == 0)
+            for (; next_q < 4; ++next_q) mbar_wait(bar_a_ready + 8 * next_q, a_phase, 2 + next_q);
+          uint32_t fresh = 0u;
+          for (int s = s0; s < s0 + n_layer_steps; ++s) {
             const Step st = s_steps[s];
-            // quarters [0, q_need) must be ready.  Layer 0 reads the input encoding only: its four barriers complete together, and
-            // all of them are consumed up front (never after the commit: the epilogue's arrivals for layer 1 must not overtake)
-            const int kb_end = (int)st.a_kb + (int)st.n_kb - 1;
-            const int q_need = l == 0 ? 4 : ((st.a_kb >= 1 && kb_end <= 4) ? kb_end : 1);
-            for (; next_q < q_need; ++next_q) mbar_wait(bar_a_ready + 8 * next_q, a_phase, 2 + next_q);   // (CTA-scope acquire: a cluster-scope one invalidates the L1)
-            if (s == s0) ANI_TRACE(8 + 16 * l + 5);
-            const uint32_t stage = g % C::STAGES, phase = (g / C::STAGES) & 1u;
-            mbar_wait(bar_full + 8 * stage, phase, 3);   // TMA-written operands: CTA-scope acquire is enough for the async proxy
+            const bool hi_stage = (st.flags & STEP_HI) != 0, lo_stage = NPASS == 3 && (st.flags & STEP_LO) != 0;
+            const uint32_t per_kb = blk * ((hi_stage ? 1u : 0u) + (lo_stage ? 1u : 0u));
+            mbar_wait(bar_full + 8 * stage, full_phase, 3);   // TMA-written operands: CTA-scope acquire is enough for the async proxy
             tc_fence_after();
-            const uint32_t b_stage = smem_u32(ring + stage * STAGE_BYTES);
-            const uint32_t blk = (uint32_t)(n_pad / PAIR) * 128u;                       // one K-block of this CTA's weight rows
-            const uint32_t per_kb = blk * (((st.flags & STEP_HI) ? 1u : 0u) + ((st.flags & STEP_LO) ? 1u : 0u));
-            if (elect_one()) {
-              // The issue loop must cost far less than the 129 cycles an MMA occupies the tensor pipe: one descriptor per operand
-              // block, then a constant 32-byte step per K=16 slice (+2 in the descriptor's address field), fully unrolled.
-              uint32_t fresh = (st.flags & STEP_FIRST) ? 0u : 1u;
-              const bool hi_stage = (st.flags & STEP_HI) != 0, lo_stage = NPASS == 3 && (st.flags & STEP_LO) != 0;
-              for (int kb = 0; kb < (int)st.n_kb; ++kb) {
-                const uint32_t a_off = (uint32_t)(st.a_kb + kb) * KB_BYTES;
-                const uint32_t b_hi = b_stage + (uint32_t)kb * per_kb;
+            if (s == s0) ANI_TRACE(8 + 16 * l + 5);
+            uint32_t b_blk = ring_u32 + stage * STAGE_BYTES;
+            for (int kb = 0; kb < (int)st.n_kb; ++kb, b_blk += per_kb) {
+              const int akb = (int)st.a_kb + kb;
+              const bool hidden = akb >= KB_HID0 && akb < KB_HID0 + 4;
+              const uint64_t bdh = smem_desc_sw128(b_blk);
+              const uint64_t bdl = smem_desc_sw128(b_blk + (hi_stage ? blk : 0u));
+              if (hidden) {
+                // A from tensor memory: quarter q of the PREVIOUS layer's accumulator buffer, re-quantised in place by its epilogue.
+                // Slice k (16 K elements): the thread that owns columns [64q + 32 (k/2), +32) wrote the hi pairs at the start of its
+                // range and (split precision) the lo pairs 16 columns further.
+                const int q = akb - KB_HID0;
+                for (; next_q <= q; ++next_q) {
+                  mbar_wait(bar_a_ready + 8 * next_q, a_phase, 2 + next_q);   // (CTA-scope acquire: a cluster-scope one invalidates the L1)
+                  tc_fence_after();
+                }
+                const uint32_t ta = a_prev + (uint32_t)q * 64u;
+                if (hi_stage) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t tk = ta + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
+                    umma_bf16_ts<PAIR>(acc, tk, bdh + (uint64_t)(2 * k), idesc, k == 0 ? fresh : 1u);
+                    if (NPASS == 3) umma_bf16_ts<PAIR>(acc, tk + 16u, bdh + (uint64_t)(2 * k), idesc, 1u);
+                  }
+                  fresh = 1u;
+                }
+                if (lo_stage) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t tk = ta + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
+                    umma_bf16_ts<PAIR>(acc, tk, bdl + (uint64_t)(2 * k), idesc, k == 0 ? fresh : 1u);
+                  }
+                  fresh = 1u;
+                }
+              } else {
+                // the input encodings: shared-memory operand blocks (ready since the tile's start / the previous layers)
+                const bool full4 = !(kb + 1 == (int)st.n_kb && st.k16_last == 2);
+                const uint32_t a_off = akb == KB_PE ? 0u : (uint32_t)KB_BYTES;
                 const uint64_t adh = smem_desc_sw128(a_hi + a_off);
                 const uint64_t adl = smem_desc_sw128(a_lo + a_off);
-                const uint64_t bdh = smem_desc_sw128(b_hi);
-                const uint64_t bdl = smem_desc_sw128(b_hi + (hi_stage ? blk : 0u));
-                const bool full4 = !(kb + 1 == (int)st.n_kb && st.k16_last == 2);
                 if (hi_stage) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -408,10 +451,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                   fresh = 1u;
                 }
               }
-              umma_commit<PAIR>(bar_empty + 8 * stage);            // frees the ring stage (both CTAs) once these MMAs retire
-              if (st.flags & STEP_LAST) umma_commit<PAIR>(bar_acc);   // layer done: its accumulator is ready
             }
-            __syncwarp();
+            umma_commit<PAIR>(bar_empty + 8 * stage);            // frees the ring stage (both CTAs) once these MMAs retire
+            if (st.flags & STEP_LAST) umma_commit<PAIR>(bar_acc);   // layer done: its accumulator is ready
+            if (++stage == C::STAGES) {
+              stage = 0;
+              full_phase ^= 1u;
+            }
           }
           ANI_TRACE(8 + 16 * l + 6);
           for (; next_q < 4; ++next_q) mbar_wait(bar_a_ready + 8 * next_q, a_phase, 7);   // keep every quarter's phase in step
@@ -457,7 +503,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     bool nvalid = false;
     float nx = 0.f, ny = 0.f, nz = 0.f;
     for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-      const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
+      const bool tracing = args.trace && blockIdx.x < 2 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
+      unsigned long long *const trace_base = args.trace + (blockIdx.x == 1 ? 256 : 0);     // the peer CTA of cluster 0: slots 256.. (its own clock)
       if (args.trace && blockIdx.x == 0 && threadIdx.x == 0 && ut / n_units < 90) args.trace[160 + ut / n_units] = (unsigned long long)clock64();
       int64_t gi;
       bool valid;
@@ -581,23 +628,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             }
             if (half == 0) write_pe<NPASS, 4, 0, 2>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
             else write_pe<NPASS, 4, 2, 4>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
+            fence_proxy_async();           // (shared-memory operand: visible to the tensor core before this layer's publishes)
           }
-          // hidden layer: bias + ReLU -> bf16 (hi/lo) -> A K-blocks 1..4 in place, one 64-column quarter (= one K-block of the
-          // next layer) at a time; this thread: 32 of the quarter's columns.  Software-pipelined: the TMEM load of quarter q+1
-          // is in flight while quarter q is converted, stored and published.
+          // hidden layer: bias + ReLU -> bf16 pairs (hi / lo) -> written with tcgen05.st over the accumulator columns just read, one
+          // 64-column quarter (= one K-block of the next layer) at a time; this thread: 32 of the quarter's columns [c, c+32):
+          // hi pairs -> columns [c, c+16), lo pairs (split precision) -> [c+16, c+32).  Software-pipelined: the TMEM load of
+          // quarter q+1 is in flight while quarter q is converted, stored and published.
           uint32_t va[32], vb[32];
           auto process = [&](const uint32_t (&v)[32], int q) {
             const int col0 = q * 64 + half * 32;               // first output column of this thread's group
+            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              float x[8];
               const float4 b0 = *reinterpret_cast<const float4 *>(bias + col0 + j4 * 8);
               const float4 b1 = *reinterpret_cast<const float4 *>(bias + col0 + j4 * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float x[8];
               if (NPASS == 1 && !alpha_layer) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j4 * 8 + j]) + bb[j];
-                store_chunk<NPASS, NPASS == 1>(a_hi, a_lo, HID_CHUNK0 + q * 8 + half * 4 + j4, row, x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hi[j4 * 4 + j] = pack_bf16_relu(x[2 * j], x[2 * j + 1]);      // the ReLU rides on the conversion
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[j4 * 8 + j]) + bb[j], 0.f);
@@ -615,14 +666,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                   sg = fmaf(x[7], w1.w, sg);
                   sigma = sg;
                 }
-                store_chunk<NPASS>(a_hi, a_lo, HID_CHUNK0 + q * 8 + half * 4 + j4, row, x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  hi[j4 * 4 + j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+                  if (NPASS == 3) lo[j4 * 4 + j] = pack_bf16_residual(x[2 * j], x[2 * j + 1], hi[j4 * 4 + j]);
+                }
               }
+            }
+            if (!(args.debug & 2)) {
+              tmem_st16(t_acc + col0, hi);
+              if (NPASS == 3) tmem_st16(t_acc + col0 + 16, lo);
             }
           };
           // publish the K-block written so far
           auto publish = [&](int q) {
+            tmem_st_wait();
             tc_fence_before();
-            fence_proxy_async();
             arrive_warp(q);
           };
           tmem_ld32(t_acc + half * 32, va);
@@ -651,7 +710,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           tmem_ld32(t_acc, v);
           tmem_ld_wait();
           tc_fence_before();
-          float *scr = reinterpret_cast<float *>(a_hi + KB_BYTES);   // exchange scratch: the hidden K-blocks (all their readers have retired)
+          float *scr = reinterpret_cast<float *>(smem + C::OFF_SCR);   // exchange scratch of the row's two threads
           constexpr int HB = ANINERF_N_BONES / 2;
           const int k0 = half * HB;
           float bw[HB];
@@ -708,7 +767,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               args.tpts_out[3 * gi + 2] = (c20 * qx + c21 * qy + c22 * qz) * inv;
             }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // the scratch is overwritten by the next tile's layer-0 epilogue
+          asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");   // the scratch is rewritten by the next tile's head
         } else if (args.density_only) {
           // ---- density query (TPoseHuman.calculate_alpha): the trunk's last layer, alpha_fc as an fp32 dot; no colour branch ----
           float sg = 0.f;
@@ -890,7 +949,8 @@ static int describe_layers(int field, const aninerf_layer *L, int n_layers, std:
 static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, int npass, bool nerf, FieldImage &im, cudaStream_t st) {
   std::vector<Step> steps;
   std::vector<uint8_t> image;
-  const int view_kb = (nerf && npass == 1) ? VIEW_CHUNK0 / 8 : PE_CHUNK0 / 8;      // see Cfg::VIEW_SEP
+  const int view_kb = KB_VIEW;
+  (void)nerf;
   const int planes = npass == 3 ? 2 : 1;
   for (size_t l = 0; l < H.size(); ++l) {
     const HostLayer &h = H[l];
@@ -1006,6 +1066,10 @@ static int fill_field(const aninerf_net *net, int field, int precision, MlpArgs 
   a.f.bias = f.bias;
   a.f.head = f.head;
   a.trace = (g_trace_field < 0 || g_trace_field == field) ? g_trace : nullptr;
+  {
+    static const char *dbg = getenv("ANINERF_DEBUG_MLP");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   a.trace_iter = g_trace_iter;
   return ANINERF_OK;
 }

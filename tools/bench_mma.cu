@@ -126,6 +126,8 @@ __device__ __forceinline__ uint32_t instr_desc(int n, int m) {
 }
 
 enum { SRC_SS_NONE = 0, SRC_SS_SW128 = 1, SRC_TS = 2 };
+__device__ int g_commit_every = 0;      // > 0: tcgen05.commit to a scratch mbarrier after every n MMAs (as a weight ring does per stage)
+__device__ int g_wait_every = 0;        // > 0: the issuing thread also try_waits an already-completed mbarrier every n MMAs
 enum { SIDE_NONE = 0, SIDE_LD_STS = 1, SIDE_LD_STTM = 2, SIDE_LD_ONLY = 3 };
 
 struct Result {
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(320, 1) mma_kernel(int src, int n, int n_mma, 
   for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3f803f80u + (i * 2654435761u & 0x007f007fu);
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
     done_flag = 0;
     side_iters = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,12 +188,14 @@ __global__ void __launch_bounds__(320, 1) mma_kernel(int src, int n, int n_mma, 
       const uint32_t idesc = instr_desc(n, 128 * PAIR);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       const int nb = n / PAIR;                                  // B rows held by each CTA
+      const int commit_every = g_commit_every, wait_every = g_wait_every;
       t0 = clock64();
       for (int i = 0; i < n_mma; ++i) {
         const int k = i & 15;                                   // K=16 slice of the K=256 operand
         uint64_t bd;
         if (src == SRC_SS_SW128) bd = desc_sw128(b0 + (k >> 2) * (nb * 128) + (k & 3) * 32);
         else bd = desc_none(b0 + k * 2 * (nb * 16), nb * 16, 128);
+        if (wait_every > 0 && (i & (wait_every - 1)) == 0) (void)mbar_try_wait(smem_u32(&bars[2]), 1);       // (powers of two: no division in the issue loop)
         if (src == SRC_TS) {
           umma_ts<PAIR>(tmem, tmem + 256 + k * 8, bd, idesc, i ? 1u : 0u);
         } else {
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(320, 1) mma_kernel(int src, int n, int n_mma, 
           else ad = desc_none(a0 + k * 2 * 2048, 2048, 128);
           umma_ss<PAIR>(tmem, ad, bd, idesc, i ? 1u : 0u);
         }
+        if (commit_every > 0 && (i & (commit_every - 1)) == commit_every - 1) umma_commit<PAIR>(smem_u32(&bars[1]));
       }
       umma_commit<PAIR>(smem_u32(&bars[0]));
       const long long t_issued = clock64();
@@ -566,6 +573,24 @@ int main(int argc, char **argv) {
       snprintf(name, sizeof(name), "cta_group::1 M=128, %s", srcs[src]);
       run_mma<1>(name, src, n, NM, SIDE_NONE, 0, clusters, d_res);
     }
+  printf("## 1b. the same with a tcgen05.commit (and an mbarrier try_wait by the issuing thread) every n MMAs, as a weight ring does per stage\n");
+  for (int every : {0, 4, 8, 64}) {
+    CK(cudaMemcpyToSymbol(g_commit_every, &every, sizeof(int)));
+    for (int w : {0, 1}) {
+      const int we = w ? every : 0;
+      CK(cudaMemcpyToSymbol(g_wait_every, &we, sizeof(int)));
+      for (int src : {1, 2}) {
+        char name[96];
+        snprintf(name, sizeof(name), "commit every %d%s, %s", every, w ? " + try_wait" : "", srcs[src]);
+        run_mma<2>(name, src, 256, NM, SIDE_NONE, 0, clusters, d_res);
+      }
+    }
+  }
+  {
+    const int zero = 0;
+    CK(cudaMemcpyToSymbol(g_commit_every, &zero, sizeof(int)));
+    CK(cudaMemcpyToSymbol(g_wait_every, &zero, sizeof(int)));
+  }
   printf("## 2. MMA rate with epilogue-like traffic next to it (aux = side iterations of 4 KB per warp while %d MMAs ran)\n", 1024);
   const char *sides[4] = {"", "8 warps tcgen05.ld + st.shared + fence", "8 warps tcgen05.ld + tcgen05.st", "8 warps tcgen05.ld only"};
   for (int src : {0, 2})

@@ -194,7 +194,7 @@ def trace_frame():
     batch = synthetic.make_render_batch(frame, ray_o, ray_d, near, far, device=dev)
     r.render_device(batch, want_bw=False)
     torch.cuda.synchronize()
-    buf = torch.zeros(256, dtype=torch.int64, device=dev)
+    buf = torch.zeros(512, dtype=torch.int64, device=dev)
     for name, field in (('BW x3 (frame)', 0), ('NERF x1 (frame)', 2)):
         os.environ['ANINERF_TRACE_FIELD'] = str(field)
         buf.zero_()
@@ -202,7 +202,14 @@ def trace_frame():
         r.render_device(batch, want_bw=False)
         torch.cuda.synchronize()
         _lib.lib().aninerf_debug_set_trace(None)
-        print_trace(name, buf.cpu().numpy())
+        t = buf.cpu().numpy()
+        print_trace(name, t)
+        st = t[320:448].reshape(16, 8)
+        say(f'{name} layer-2 issue timeline per step (top, a_ready ok, full ok, issued; relative to tile start): ' +
+            ' | '.join(f'{int(r[0] - t[0])} {int(r[1] - r[0])} {int(r[2] - r[1])} {int(r[3] - r[2])}' for r in st if r[0]))
+        tp = t[256:]
+        say(f'{name} PEER CTA rows (own clock, relative to its tile start): ' + ' | '.join(
+            f'L{l} woke {tp[8 + 16 * l + 1] - tp[0]} done {tp[8 + 16 * l + 2] - tp[0] if tp[8 + 16 * l + 2] else 0}' for l in range(9)))
 
 
 if 'trace' in sys.argv[1:]:

@@ -29,6 +29,8 @@ san)
   done;;
 trace)
   timeout 300 python tools/gpu_diag.py trace_frame > gpurun_out/trace_$tag.log 2>&1; echo "trace rc=$?"; grep -A40 "trace_frame" gpurun_out/trace_$tag.log | head -90;;
+dbg)
+  for d in 1 2 3; do ANINERF_DEBUG_MLP=$d timeout 300 python tools/gpu_diag.py trace_frame > gpurun_out/trace_dbg${d}_$tag.log 2>&1; echo "dbg $d rc=$?"; grep -A22 "trace_frame" gpurun_out/trace_dbg${d}_$tag.log | grep "mean period\|L[1234] slot0"; done;;
 ncu)
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > gpurun_out/ncu_launch_$tag.log 2>&1; echo "ncu list rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:'mlp_kernel' --launch-skip 12 -c 4 -o gpurun_out/prof_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > gpurun_out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?";;
