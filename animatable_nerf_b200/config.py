@@ -11,6 +11,7 @@ DEFAULTS = dict(
     N_samples=64, N_rand=1024, perturb=1.0, norm_th=0.05, train_th=0.0, white_bkgd=False, raw_noise_std=0,
     xyz_res=10, view_res=4, box_padding=0.05, voxel_size=[0.005, 0.005, 0.005],
     test_novel_pose=False, aninerf_animation=False, num_train_frame=60, num_eval_frame=1000,
+    mesh_th=50.0,             # lib/config/config.py:45 (aninerf_s9p.yaml:153 overrides it with 5.)
     # knobs of this implementation (unknown keys are legal in the reference's yacs fork)
     b200_bw_precision=3,      # 3: bf16x3 split products (fp32-equivalent) / 1: single bf16 pass
     b200_nerf_precision=1,

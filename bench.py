@@ -345,6 +345,18 @@ def other_configs(dev, frame, rank, world):
     ms = _time_ms(lambda: sweep.query_density_grid(net5, fb, pts, None, rank, world), reps=2, warm=1)
     out['config5_density_grid_256^3'] = {'ms': ms, 'points_per_s': pts.shape[0] * pts.shape[1] * pts.shape[2] / (ms * 1e-3),
                                          'grid': list(pts.shape[:3])}
+    # ... and the mesh of that cube (aninerf_mesh_renderer.py:39-40: pad 10, marching cubes) on the GPU
+    from animatable_nerf_b200 import aninerf_mesh_renderer as mesh
+    cube = sweep.query_density_grid(net5, fb, pts, None, rank, world)
+    th = float(cube.max()) * 0.5                                   # random-init densities are small: put the iso level inside their range
+    padded = torch.nn.functional.pad(cube, (mesh.PAD,) * 6)
+    v, t = mesh.marching_cubes(padded, th)
+    ms = _time_ms(lambda: mesh.marching_cubes(padded, th), reps=3, warm=1)
+    npts = padded.numel()
+    out['config5_marching_cubes_276^3'] = {'ms': ms, 'grid_points_per_s': npts / (ms * 1e-3), 'vertices': int(v.shape[0]), 'triangles': int(t.shape[0]),
+                                           'algorithmic_gbs': npts * 52 / (ms * 1e-3) / 1e9,
+                                           'note': 'classify + scan + emit, incl. the host read of the mesh size; 52 B per grid point algorithmic (DESIGN.md)'}
+    del cube, padded, v, t
     # ---- active-fraction sweep: the headline frame at norm_th 0.05 (the reference's value) / 0.1 / 0.2.  FLOPs scale with the ACTIVE
     # samples, nominal samples/s therefore falls as the shell around the body surface thickens ------------------------------------
     K, R, T = synthetic.make_camera(frame, 1024, 1024)
@@ -589,16 +601,25 @@ def run_b200(args):
     dom = max(cand, key=lambda k: stage_ms.get(k, 0.0))
     dom_tflops = n_active * cand[dom] / (stage_ms[dom] * 1e-3) / 1e12
     mlp_ms = stage_ms.get('bw_field_posed', 0.0) + stage_ms.get('nerf_field', 0.0)
+    is_bw = dom == 'bw_field_posed'
+    exec_flop = EXEC_FLOP_BW if is_bw else EXEC_FLOP_NERF
+    kprefix = 'mlp_kernel<3, 0' if is_bw else 'mlp_kernel<1, 1'
     roofline = {
-        'bound': 'tensor', 'kernel': 'mlp_kernel<3,false> (blend-weight field, bf16x3)' if dom == 'bw_field_posed' else 'mlp_kernel<1,true> (NeRF field, bf16)',
+        'bound': 'tensor', 'kernel': 'mlp_kernel<3,false> (blend-weight field, bf16x3)' if is_bw else 'mlp_kernel<1,true> (NeRF field, bf16)',
         'achieved': dom_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': dom_tflops / pk['bf16_tflops_sustained'],
-        'traffic': ncu_traffic('mlp_kernel<3, 0' if dom == 'bw_field_posed' else 'mlp_kernel<1, 1'), 'traffic_unit': 'DRAM bytes per launch (ncu --set full, profiles/)',
+        'traffic': ncu_traffic(kprefix), 'traffic_unit': 'DRAM bytes per launch (ncu --set full, profiles/)',
         'peak_source': pk['source'] + ' (sustained bf16: kernel timed inside the step)',
         'algorithmic_flop_per_active_sample': cand[dom], 'active_samples_per_launch': n_active, 'launch_ms': stage_ms[dom],
-        'executed': {'note': 'tensor-core FLOP the kernel issues (bf16x3 = 3 passes, folded layer shapes); frac of the sustained cuBLAS bf16 rate',
-                     'tflops': n_active * (EXEC_FLOP_BW if dom == 'bw_field_posed' else EXEC_FLOP_NERF) / (stage_ms[dom] * 1e-3) / 1e12,
-                     'frac': n_active * (EXEC_FLOP_BW if dom == 'bw_field_posed' else EXEC_FLOP_NERF) / (stage_ms[dom] * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
-                     'tensor_pipe_active_pct_ncu': ncu_traffic('mlp_kernel<3, 0' if dom == 'bw_field_posed' else 'mlp_kernel<1, 1', 'tensor_pipe_active_pct')},
+        # what the kernel EXECUTES (bf16x3 = 3 tensor-core passes of the folded layer shapes).  The honest utilisation figure is ncu's
+        # tensor-pipe-active percentage of the same kernel (profiles/rNN_ncu_full_summary.md); the ratio to a cuBLAS rate is given
+        # against the BURST rate (the sustained one is measured at a power-throttled clock this kernel does not run at)
+        'executed': {'tflops': n_active * exec_flop / (stage_ms[dom] * 1e-3) / 1e12,
+                     'frac_of_burst_bf16': n_active * exec_flop / (stage_ms[dom] * 1e-3) / 1e12 / pk['bf16_tflops'],
+                     'tensor_pipe_active_pct_ncu': ncu_traffic(kprefix, 'tensor_pipe_active_pct')},
+        'other_mlp': {'kernel': 'mlp_kernel<1,true> (NeRF field, bf16)' if is_bw else 'mlp_kernel<3,false> (blend-weight field)',
+                      'launch_ms': stage_ms.get('nerf_field' if is_bw else 'bw_field_posed'),
+                      'achieved_tflops': n_active * (FLOP_NERF if is_bw else FLOP_BW) / (stage_ms.get('nerf_field' if is_bw else 'bw_field_posed', 1e9) * 1e-3) / 1e12,
+                      'tensor_pipe_active_pct_ncu': ncu_traffic('mlp_kernel<1, 1' if is_bw else 'mlp_kernel<3, 0', 'tensor_pipe_active_pct')},
         'both_mlps': {'tflops': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 if mlp_ms else None,
                       'frac': n_active * (FLOP_BW + FLOP_NERF) / (mlp_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'] if mlp_ms else None},
     }

@@ -376,6 +376,16 @@ int aninerf_gather_selected_rows(const uint8_t *sel, const int32_t *chunk_offset
 int aninerf_bw_loss(const float *pbw, const float *tbw, const uint8_t *sel, const int32_t *n_sel, int64_t n, float *loss, float *d_pbw,
                     float *d_tbw, void *stream);
 
+/* Mesh extraction from the density cube: `mcubes.marching_cubes(cube, cfg.mesh_th)` of
+ * lib/networks/renderer/aninerf_mesh_renderer.py:40 (PyMCubes 0.1.0: Lorensen-Cline marching cubes, corner bit set when
+ * value <= iso, vertices linearly interpolated in float64 index coordinates).  cube: device (X,Y,Z) float32, x-major.
+ * verts: device (cap_verts,3) float64, ordered by owning grid point then axis; tris: device (cap_tris,3) int32 indices into verts,
+ * ordered by cell then case-table order, wound towards the <= iso side.  counts: device int32[2] = {vertices, triangles} the
+ * cube yields -- when a count exceeds its capacity the surplus was dropped: read the counts, enlarge, call again. */
+int64_t aninerf_marching_cubes_workspace_bytes(int32_t X, int32_t Y, int32_t Z);
+int aninerf_marching_cubes(const float *cube, int32_t X, int32_t Y, int32_t Z, double iso, double *verts, int64_t cap_verts,
+                           int32_t *tris, int64_t cap_tris, int32_t *counts, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Optional per-stage device timing of aninerf_render_rays (CUDA events on the launching stream).
  * Stage order: split volumes, clear raw, mask+scan+compact front end, (unused), (unused), blend-weight
  * field at posed points (+LBS), blend-weight field at canonical points, NeRF field (+tail), compositing.
