@@ -52,42 +52,60 @@ struct GemmSmem {
   static constexpr int BYTES = G_STAGES * STAGE + 64;
 };
 
-// stage one K chunk of an operand: rows [r0, r0+ROWS) x k [k0, k0+32) of X (zero outside [0,R) x [0,K))
+// One K chunk of an operand -- rows [r0, r0+ROWS) x k [k0, k0+32) of X (zero outside [0,R) x [0,K)) -- in two steps, so that the
+// global loads of chunk c+1 are in flight while chunk c is converted, published and multiplied:
+//   load():  global fp32 -> registers;   store(): registers -> bf16 hi/lo -> shared memory (UMMA no-swizzle K-major core matrices)
 template <int ROWS>
-__device__ __forceinline__ void stage_operand(uint8_t *hi, uint8_t *lo, const float *X, long long rs, long long ks, int r0, int R, int k0,
-                                              int K) {
-  constexpr int TASKS = ROWS * (G_KC / 8);
-  const bool row_contig = rs == 1 && ks != 1;   // consecutive threads walk the contiguous direction
+struct OperandChunk {
+  static constexpr int TASKS = ROWS * (G_KC / 8);
+  static constexpr int PER_THREAD = (TASKS + G_THREADS - 1) / G_THREADS;
+  float x[PER_THREAD][8];
+
+  __device__ __forceinline__ void load(const float *X, long long rs, long long ks, int r0, int R, int k0, int K) {
+    const bool row_contig = rs == 1 && ks != 1;   // consecutive threads walk the contiguous direction
 #pragma unroll
-  for (int t = threadIdx.x; t < TASKS; t += G_THREADS) {
-    const int row = row_contig ? t % ROWS : t / (G_KC / 8);
-    const int kg = row_contig ? t / ROWS : t % (G_KC / 8);
-    const int r = r0 + row, k = k0 + kg * 8;
-    float x[8];
-    const float *src = X + (long long)r * rs + (long long)k * ks;
-    if (ks == 1 && r < R && k + 8 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-      // K-contiguous, 16-byte aligned, fully inside: two float4 loads
-      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src)), v1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
-      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-      x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-    } else {
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int t = threadIdx.x + i * G_THREADS;
+      if (TASKS % G_THREADS != 0 && t >= TASKS) break;
+      const int row = row_contig ? t % ROWS : t / (G_KC / 8);
+      const int kg = row_contig ? t / ROWS : t % (G_KC / 8);
+      const int r = r0 + row, k = k0 + kg * 8;
+      const float *src = X + (long long)r * rs + (long long)k * ks;
+      if (ks == 1 && r < R && k + 8 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        // K-contiguous, 16-byte aligned, fully inside: two float4 loads
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src)), v1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+        x[i][0] = v0.x; x[i][1] = v0.y; x[i][2] = v0.z; x[i][3] = v0.w;
+        x[i][4] = v1.x; x[i][5] = v1.y; x[i][6] = v1.z; x[i][7] = v1.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = (r < R && k + j < K) ? __ldg(src + (long long)j * ks) : 0.f;
+        for (int j = 0; j < 8; ++j) x[i][j] = (r < R && k + j < K) ? __ldg(src + (long long)j * ks) : 0.f;
+      }
     }
-    uint4 h, l;
-    h.x = pack_bf16(x[0], x[1]);
-    h.y = pack_bf16(x[2], x[3]);
-    h.z = pack_bf16(x[4], x[5]);
-    h.w = pack_bf16(x[6], x[7]);
-    l.x = pack_bf16_residual(x[0], x[1], h.x);
-    l.y = pack_bf16_residual(x[2], x[3], h.y);
-    l.z = pack_bf16_residual(x[4], x[5], h.z);
-    l.w = pack_bf16_residual(x[6], x[7], h.w);
-    const int off = kg * (ROWS * 16) + row * 16;
-    *reinterpret_cast<uint4 *>(hi + off) = h;
-    *reinterpret_cast<uint4 *>(lo + off) = l;
   }
-}
+
+  __device__ __forceinline__ void store(uint8_t *hi, uint8_t *lo, long long rs, long long ks) const {
+    const bool row_contig = rs == 1 && ks != 1;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int t = threadIdx.x + i * G_THREADS;
+      if (TASKS % G_THREADS != 0 && t >= TASKS) break;
+      const int row = row_contig ? t % ROWS : t / (G_KC / 8);
+      const int kg = row_contig ? t / ROWS : t % (G_KC / 8);
+      uint4 h, l;
+      h.x = pack_bf16(x[i][0], x[i][1]);
+      h.y = pack_bf16(x[i][2], x[i][3]);
+      h.z = pack_bf16(x[i][4], x[i][5]);
+      h.w = pack_bf16(x[i][6], x[i][7]);
+      l.x = pack_bf16_residual(x[i][0], x[i][1], h.x);
+      l.y = pack_bf16_residual(x[i][2], x[i][3], h.y);
+      l.z = pack_bf16_residual(x[i][4], x[i][5], h.z);
+      l.w = pack_bf16_residual(x[i][6], x[i][7], h.w);
+      const int off = kg * (ROWS * 16) + row * 16;
+      *reinterpret_cast<uint4 *>(hi + off) = h;
+      *reinterpret_cast<uint4 *>(lo + off) = l;
+    }
+  }
+};
 
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_constant__ GemmDev g) {
@@ -116,32 +134,45 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_cons
     k_lo = blockIdx.z * g.k_per_split;
     k_hi = min(g.K[0], k_lo + g.k_per_split);
   }
+  // the chunk list: segment 0 over [k_lo, k_hi), then segment 1 over [0, K1)
+  const int n0_chunks = (max(k_hi - k_lo, 0) + G_KC - 1) / G_KC;
+  const int n1_chunks = g.n_seg > 1 ? (g.K[1] + G_KC - 1) / G_KC : 0;
+  const int n_chunks = n0_chunks + n1_chunks;
+  OperandChunk<G_BM> ra;
+  OperandChunk<BN> rb;
+  auto load_chunk = [&](int c) {
+    const int seg = c < n0_chunks ? 0 : 1;
+    const int k0 = seg == 0 ? k_lo + c * G_KC : (c - n0_chunks) * G_KC;
+    const int ke = seg == 0 ? k_hi : g.K[1];
+    ra.load(g.A[seg], g.a_rs[seg], g.a_ks[seg], m0, g.M, k0, ke);
+    rb.load(g.B[seg], g.b_rs[seg], g.b_ks[seg], n0, g.N, k0, ke);
+  };
+  if (n_chunks > 0) load_chunk(0);
   int chunk = 0;
-  for (int seg = 0; seg < g.n_seg; ++seg) {
-    const int kb = seg == 0 ? k_lo : 0, ke = seg == 0 ? k_hi : g.K[seg];
-    for (int k0 = kb; k0 < ke; k0 += G_KC, ++chunk) {
-      const int s = chunk % G_STAGES;
-      if (chunk >= G_STAGES) mbar_wait(bar0 + 8 * s, (uint32_t)((chunk / G_STAGES - 1) & 1), 20);   // MMAs of chunk - STAGES have read the stage
-      uint8_t *base = smem + s * S::STAGE;
-      uint8_t *a_hi = base, *a_lo = base + S::A_STAGE, *b_hi = base + 2 * S::A_STAGE, *b_lo = b_hi + S::B_STAGE;
-      stage_operand<G_BM>(a_hi, a_lo, g.A[seg], g.a_rs[seg], g.a_ks[seg], m0, g.M, k0, ke);
-      stage_operand<BN>(b_hi, b_lo, g.B[seg], g.b_rs[seg], g.b_ks[seg], n0, g.N, k0, ke);
-      fence_proxy_async();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
+  for (; chunk < n_chunks; ++chunk) {
+    const int s = chunk % G_STAGES;
+    const int seg = chunk < n0_chunks ? 0 : 1;
+    if (chunk >= G_STAGES) mbar_wait(bar0 + 8 * s, (uint32_t)((chunk / G_STAGES - 1) & 1), 20);   // MMAs of chunk - STAGES have read the stage
+    uint8_t *base = smem + s * S::STAGE;
+    uint8_t *a_hi = base, *a_lo = base + S::A_STAGE, *b_hi = base + 2 * S::A_STAGE, *b_lo = b_hi + S::B_STAGE;
+    ra.store(a_hi, a_lo, g.a_rs[seg], g.a_ks[seg]);
+    rb.store(b_hi, b_lo, g.b_rs[seg], g.b_ks[seg]);
+    if (chunk + 1 < n_chunks) load_chunk(chunk + 1);          // in flight while this chunk is published and multiplied
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < G_KC / 16; ++k) {
-          const uint64_t ah = smem_desc(smem_u32(a_hi) + k * 2 * (G_BM * 16), G_BM * 16, 128);
-          const uint64_t al = smem_desc(smem_u32(a_lo) + k * 2 * (G_BM * 16), G_BM * 16, 128);
-          const uint64_t bh = smem_desc(smem_u32(b_hi) + k * 2 * (BN * 16), BN * 16, 128);
-          const uint64_t bl = smem_desc(smem_u32(b_lo) + k * 2 * (BN * 16), BN * 16, 128);
-          umma_bf16<1>(tmem, ah, bh, idesc, (chunk == 0 && k == 0) ? 0u : 1u);
-          umma_bf16<1>(tmem, al, bh, idesc, 1u);
-          umma_bf16<1>(tmem, ah, bl, idesc, 1u);
-        }
-        umma_commit<1>(bar0 + 8 * s);
+      for (int k = 0; k < G_KC / 16; ++k) {
+        const uint64_t ah = smem_desc(smem_u32(a_hi) + k * 2 * (G_BM * 16), G_BM * 16, 128);
+        const uint64_t al = smem_desc(smem_u32(a_lo) + k * 2 * (G_BM * 16), G_BM * 16, 128);
+        const uint64_t bh = smem_desc(smem_u32(b_hi) + k * 2 * (BN * 16), BN * 16, 128);
+        const uint64_t bl = smem_desc(smem_u32(b_lo) + k * 2 * (BN * 16), BN * 16, 128);
+        umma_bf16<1>(tmem, ah, bh, idesc, (chunk == 0 && k == 0) ? 0u : 1u);
+        umma_bf16<1>(tmem, al, bh, idesc, 1u);
+        umma_bf16<1>(tmem, ah, bl, idesc, 1u);
       }
+      umma_commit<1>(bar0 + 8 * s);
     }
   }
   if (threadIdx.x == 0) umma_commit<1>(bar0 + 8 * G_STAGES);   // arrives once every MMA above has retired

@@ -255,36 +255,75 @@ __global__ void __launch_bounds__(256) world_to_pose_kernel(const float *__restr
 // =============================================================================================
 // 6. blend-weight volume sampling (blend_utils.py:119-149), all 25 channels, reference layout
 // =============================================================================================
-// One warp per point-group: each lane owns one channel (25 of 32 lanes active) so that the 8 corner
-// rows (100 B each) are read with coalesced 100-byte requests; out (n,25) rows likewise.
+// One warp per group of 32 points.  Phase 1 (lane = point): the bit-exact trilinear corner set (weights and voxel offsets in ATen's
+// order) of each point goes to shared memory.  Phase 2 (lane = channel, 25 of 32 lanes): per point the 16 words are read back with four
+// broadcast LDS.128, then the 8 corner rows (100 B each) are read with coalesced 100-byte requests and accumulated in ATen's order;
+// out (n,25) rows likewise.  Two points are in flight per iteration (16 independent row loads).
+// Round 1 broadcast the corner set with 16 shuffles per point: ncu (profiles/r02_stage_kernels_summary.md) showed the LSU data pipe --
+// which serves SHFL, LDS and the L1 wavefronts of LDG alike -- 87 % busy, two thirds of it shuffles.
+constexpr int SBW_STRIDE = 20;     // words per point in shared memory (16 + 4 pad: conflict-free 128-bit stores at an 80-byte stride)
 __global__ void __launch_bounds__(256) sample_bw_kernel(const float *__restrict__ pts, int64_t n, const float *__restrict__ vol,
                                                         const float *__restrict__ bounds, int X, int Y, int Z,
                                                         float *__restrict__ out) {
   __shared__ VolumeGrid g;
+  __shared__ __align__(16) float s_corner[8][32 * SBW_STRIDE];
   if (threadIdx.x < 3) {
     g.lo[threadIdx.x] = bounds[threadIdx.x];
     g.ext[threadIdx.x] = __fsub_rn(bounds[3 + threadIdx.x], bounds[threadIdx.x]);
     g.dim[threadIdx.x] = threadIdx.x == 0 ? X : (threadIdx.x == 1 ? Y : Z);
   }
   __syncthreads();
-  int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float *sc = s_corner[wib];
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t base = warp * 32; base < n; base += nwarps * 32) {
     int64_t mine = base + lane;
     float w[8];
     int off[8];
-    if (mine < n) trilinear_corners(g, pts[3 * mine], pts[3 * mine + 1], pts[3 * mine + 2], w, off);
-    int cnt = (int)min((int64_t)32, n - base);
-    for (int p = 0; p < cnt; ++p) {
-      float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float wk = __shfl_sync(0xffffffffu, w[k], p);
-        int ok = __shfl_sync(0xffffffffu, off[k], p);
-        if (ok >= 0 && lane < ANINERF_BW_CH) acc = __fadd_rn(acc, __fmul_rn(__ldg(vol + (int64_t)ok * ANINERF_BW_CH + lane), wk));
+    for (int k = 0; k < 8; ++k) {
+      w[k] = 0.f;
+      off[k] = -1;
+    }
+    if (mine < n) trilinear_corners(g, pts[3 * mine], pts[3 * mine + 1], pts[3 * mine + 2], w, off);
+    __syncwarp();                                   // the previous iteration's readers are done
+    float4 *dst = reinterpret_cast<float4 *>(sc + lane * SBW_STRIDE);
+    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_float4(__int_as_float(off[0]), __int_as_float(off[1]), __int_as_float(off[2]), __int_as_float(off[3]));
+    dst[3] = make_float4(__int_as_float(off[4]), __int_as_float(off[5]), __int_as_float(off[6]), __int_as_float(off[7]));
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, n - base);
+    const bool ch = lane < ANINERF_BW_CH;
+    for (int p = 0; p < cnt; p += 2) {
+      // two points per iteration: their 16 corner rows are independent loads
+      float wv[2][8];
+      int ov[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 *src = reinterpret_cast<const float4 *>(sc + min(p + u, cnt - 1) * SBW_STRIDE);
+        const float4 a = src[0], b = src[1], c = src[2], d = src[3];
+        wv[u][0] = a.x; wv[u][1] = a.y; wv[u][2] = a.z; wv[u][3] = a.w;
+        wv[u][4] = b.x; wv[u][5] = b.y; wv[u][6] = b.z; wv[u][7] = b.w;
+        ov[u][0] = __float_as_int(c.x); ov[u][1] = __float_as_int(c.y); ov[u][2] = __float_as_int(c.z); ov[u][3] = __float_as_int(c.w);
+        ov[u][4] = __float_as_int(d.x); ov[u][5] = __float_as_int(d.y); ov[u][6] = __float_as_int(d.z); ov[u][7] = __float_as_int(d.w);
       }
-      if (lane < ANINERF_BW_CH) out[(base + p) * ANINERF_BW_CH + lane] = acc;
+      float v[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = (ch && ov[u][k] >= 0) ? __ldg(vol + (int64_t)ov[u][k] * ANINERF_BW_CH + lane) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (p + u < cnt) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (ov[u][k] >= 0) acc = __fadd_rn(acc, __fmul_rn(v[u][k], wv[u][k]));      // (an outside corner is skipped, as ATen does)
+          if (ch) out[(base + p + u) * ANINERF_BW_CH + lane] = acc;
+        }
+      }
     }
   }
 }

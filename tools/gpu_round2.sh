@@ -22,7 +22,7 @@ mma)
   timeout 120 tools/bench_mma 74 > gpurun_out/mma74_$tag.log 2>&1; echo "mma74 rc=$?"; grep -v "^#" gpurun_out/mma74_$tag.log | head -40;;
 stage)
   timeout 300 python tools/stage_kernels.py > gpurun_out/stage_$tag.log 2>&1; echo "stage rc=$?"; tail -4 gpurun_out/stage_$tag.log
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'sample_bw_kernel|lbs_kernel|composite_kernel' --launch-skip 9 -c 9 -o gpurun_out/prof_stage_$tag -f python tools/stage_kernels.py > gpurun_out/ncu_stage_$tag.log 2>&1; echo "ncu stage rc=$?";;
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'sample_bw_kernel|lbs_kernel|composite_kernel' --launch-skip 4 -c 17 -o gpurun_out/prof_stage_$tag -f python tools/stage_kernels.py > gpurun_out/ncu_stage_$tag.log 2>&1; echo "ncu stage rc=$?";;
 san)
   for tool in memcheck synccheck racecheck; do
     timeout 420 compute-sanitizer --tool $tool --print-limit 30 python tools/sanitize_frame.py > gpurun_out/san_${tool}_$tag.log 2>&1; echo "sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|SANITIZE_FRAME_DONE|Error|hazard" gpurun_out/san_${tool}_$tag.log | head -8
