@@ -122,6 +122,7 @@ PROTOTYPES = {
     'aninerf_select_rows': (_I32, [_VP, _VP, _I32, _F, _VP, _VP, _VP]),
     'aninerf_gather_selected_rows': (_I32, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
     'aninerf_bw_loss': (_I32, [_VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    'aninerf_knn_blend_weights': (_I32, [_VP, _I64, _VP, _I32, _VP, _I32, _F, _VP, _VP, _VP]),
     'aninerf_marching_cubes_workspace_bytes': (_I64, [_I32, _I32, _I32]),
     'aninerf_marching_cubes': (_I32, [_VP, _I32, _I32, _I32, C.c_double, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP]),
     'aninerf_query_workspace_bytes': (_I64, [_I64, _I64]),

@@ -634,3 +634,130 @@ int aninerf_bw_loss(const float *pbw, const float *tbw, const uint8_t *sel, cons
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// K-nearest-vertex blend weights of the extended networks:
+// sample_blend_closest_points, lib/utils/sample_utils.py:323-349 over pytorch3d.ops.knn_points (K = 5): the K nearest SMPL
+// vertices of every sample, inverse-distance weights w_k = (1/(d_k + eps)) / sum, the weighted blend weights and distance.
+// All vertices (6890 x 16 B = 110 KB) are staged in shared memory; a thread scans them for one point (warp-uniform broadcast
+// reads) keeping the K best in registers.  Squared distances are (dx*dx + dy*dy) + dz*dz, separately rounded, ties to the lower
+// vertex index -- the order of the brute-force oracle.
+// =============================================================================================
+namespace aninerf {
+
+constexpr int KNN_MAX_K = 8;
+constexpr int KNN_TILE = 7168;          // vertices per shared-memory tile (112 KB of float4)
+
+template <int K>
+__global__ void __launch_bounds__(256) knn_blend_kernel(const float *__restrict__ pts, int64_t n, const float *__restrict__ verts, int n_verts,
+                                                        const float *__restrict__ values, float eps, float *__restrict__ bw_out,
+                                                        float *__restrict__ dist_out) {
+  extern __shared__ float4 s_v[];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (live) {
+    px = pts[3 * i];
+    py = pts[3 * i + 1];
+    pz = pts[3 * i + 2];
+  }
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    bd[k] = INFINITY;
+    bi[k] = 0;
+  }
+  for (int t0 = 0; t0 < n_verts; t0 += KNN_TILE) {
+    const int cnt = min(KNN_TILE, n_verts - t0);
+    __syncthreads();
+    for (int v = threadIdx.x; v < cnt; v += blockDim.x)
+      s_v[v] = make_float4(verts[3 * (int64_t)(t0 + v)], verts[3 * (int64_t)(t0 + v) + 1], verts[3 * (int64_t)(t0 + v) + 2], 0.f);
+    __syncthreads();
+    for (int v = 0; v < cnt; ++v) {
+      const float4 q = s_v[v];
+      const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d < bd[K - 1]) {
+        // insertion into the sorted K best (strict <: an equal distance keeps the earlier vertex in front)
+        bd[K - 1] = d;
+        bi[K - 1] = t0 + v;
+#pragma unroll
+        for (int k = K - 1; k > 0; --k) {
+          if (bd[k] < bd[k - 1]) {
+            const float td = bd[k];
+            bd[k] = bd[k - 1];
+            bd[k - 1] = td;
+            const int ti = bi[k];
+            bi[k] = bi[k - 1];
+            bi[k - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+  if (!live) return;
+  // guard_knn_points: dists = sqrt(d2); disp = 1 / (dists + eps); weights = disp / sum(disp)   (sample_utils.py:311-313, 340-342)
+  float dist[K], w[K], sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    dist[k] = sqrtf(bd[k]);
+    w[k] = 1.0f / (dist[k] + eps);
+    sum += w[k];
+  }
+  float dw = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    w[k] = w[k] / sum;
+    dw = fmaf(dist[k], w[k], dw);
+  }
+  if (dist_out) dist_out[i] = dw;
+  float acc[ANINERF_N_BONES];
+#pragma unroll
+  for (int c = 0; c < ANINERF_N_BONES; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float4 *row = reinterpret_cast<const float4 *>(values + (int64_t)bi[k] * ANINERF_N_BONES);
+#pragma unroll
+    for (int q = 0; q < ANINERF_N_BONES / 4; ++q) {
+      const float4 r = __ldg(row + q);
+      acc[4 * q] = fmaf(r.x, w[k], acc[4 * q]);
+      acc[4 * q + 1] = fmaf(r.y, w[k], acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(r.z, w[k], acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(r.w, w[k], acc[4 * q + 3]);
+    }
+  }
+  float4 *o = reinterpret_cast<float4 *>(bw_out + i * ANINERF_N_BONES);
+#pragma unroll
+  for (int q = 0; q < ANINERF_N_BONES / 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+}
+
+template <int K>
+static int launch_knn(const float *pts, int64_t n, const float *verts, int n_verts, const float *values, float eps, float *bw_out, float *dist_out,
+                      cudaStream_t st) {
+  static bool configured = false;
+  const int smem = KNN_TILE * (int)sizeof(float4);
+  if (!configured) {
+    ANI_CUDA(cudaFuncSetAttribute(knn_blend_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  knn_blend_kernel<K><<<(unsigned)((n + 255) / 256), 256, smem, st>>>(pts, n, verts, n_verts, values, eps, bw_out, dist_out);
+  ANI_LAUNCHED();
+  return ANINERF_OK;
+}
+
+}  // namespace aninerf
+
+extern "C" int aninerf_knn_blend_weights(const float *pts, int64_t n, const float *verts, int32_t n_verts, const float *values, int32_t K, float eps,
+                                         float *bw_out, float *dist_out, void *stream) {
+  ANI_CHECK_ARG(pts && verts && values && bw_out && n >= 0 && n_verts >= K && K >= 1 && K <= aninerf::KNN_MAX_K);
+  ANI_CHECK_ARG((((uintptr_t)values | (uintptr_t)bw_out) & 15) == 0);
+  if (n == 0) return ANINERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (K) {
+    case 1: return aninerf::launch_knn<1>(pts, n, verts, n_verts, values, eps, bw_out, dist_out, st);
+    case 5: return aninerf::launch_knn<5>(pts, n, verts, n_verts, values, eps, bw_out, dist_out, st);
+    case 8: return aninerf::launch_knn<8>(pts, n, verts, n_verts, values, eps, bw_out, dist_out, st);
+    default: return aninerf::fail(ANINERF_EINVAL, "%s: K must be 1, 5 or 8%s", __func__);
+  }
+}

@@ -376,6 +376,14 @@ int aninerf_gather_selected_rows(const uint8_t *sel, const int32_t *chunk_offset
 int aninerf_bw_loss(const float *pbw, const float *tbw, const uint8_t *sel, const int32_t *n_sel, int64_t n, float *loss, float *d_pbw,
                     float *d_tbw, void *stream);
 
+/* K-nearest-vertex blend weights of the extended (`aligned_*`, `anisdf_*`) networks: `sample_blend_closest_points`,
+ * lib/utils/sample_utils.py:323-349 over pytorch3d.ops.knn_points.  pts (n,3), verts (n_verts,3), values (n_verts,24) 16-byte
+ * aligned; K in {1, 5, 8} (the reference uses 5), eps = 1e-8.  bw_out (n,24) = sum_k w_k values[idx_k] with
+ * w_k = (1/(d_k + eps)) / sum_j 1/(d_j + eps), d = Euclidean distance to the K nearest vertices; dist_out (n) = sum_k d_k w_k
+ * (may be NULL). */
+int aninerf_knn_blend_weights(const float *pts, int64_t n, const float *verts, int32_t n_verts, const float *values, int32_t K, float eps,
+                              float *bw_out, float *dist_out, void *stream);
+
 /* Mesh extraction from the density cube: `mcubes.marching_cubes(cube, cfg.mesh_th)` of
  * lib/networks/renderer/aninerf_mesh_renderer.py:40 (PyMCubes 0.1.0: Lorensen-Cline marching cubes, corner bit set when
  * value <= iso, vertices linearly interpolated in float64 index coordinates).  cube: device (X,Y,Z) float32, x-major.

@@ -194,6 +194,24 @@ def forward_lbs(tpts, bw, A):
     return torch.sum(M[..., :3, :3] * tpts[:, :, None], dim=3) + M[..., :3, 3]
 
 
+def sample_blend_closest_points(src, ref, values, K=5, exp=1e-8):
+    """lib/utils/sample_utils.py:323-349 (the extended networks' replacement of the volume lookup).  `knn_points` comes from
+    pytorch3d, which is absent here (SURVEY 8c stubs it): restated as the brute force its documentation defines -- squared
+    Euclidean distances, the K smallest in ascending order -- PARITY UNPINNED for that third-party piece; everything after it
+    follows the reference line by line.  src (B,n,3), ref (B,V,3), values (B,V,24) -> (B,n,24), (B,n,1)."""
+    n_batch, n_points, _ = src.shape
+    diff = src[:, :, None, :] - ref[:, None, :, :]
+    d2 = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+    d2s, idx = torch.sort(d2, dim=-1, stable=True)
+    dists, vert_ids = d2s[..., :K].sqrt(), idx[..., :K]
+    values = values.view(-1, values.shape[-1])
+    disp = 1 / (dists + exp)
+    weights = disp / disp.sum(dim=-1, keepdim=True)
+    dists = torch.einsum('ijk, ijk -> ij', dists, weights)
+    sampled = torch.einsum('ijkl, ijk -> ijl', values[vert_ids], weights)
+    return sampled.view(n_batch, n_points, -1), dists.view(n_batch, n_points, 1)
+
+
 # ----------------------------------------------------------------------------
 # stage 3: positional encoding  -- embedder.py:5-54
 # ----------------------------------------------------------------------------

@@ -246,3 +246,35 @@ def test_nerf_field(dev, case):
     ga3, gr3 = net3.tpose_human.calculate_alpha_rgb(pts.to(dev), vd.to(dev), batch['latent_index'].to(dev))
     assert (ga3.cpu() - alpha).abs().max() <= 2e-5
     assert (gr3.cpu() - rgb).abs().max() <= 2e-5
+
+
+def test_knn_blend_weights_vs_oracle(dev):
+    """sample_blend_closest_points (lib/utils/sample_utils.py:323-349, the extended networks' blend-weight lookup): 5 nearest of
+    6890 SMPL-like vertices, inverse-distance weights.  Blend weights and distance within 1e-5 of the brute-force oracle; also
+    K = 1, points ON vertices (distance 0: weight ~1/eps), a ragged point count and a vertex count that needs three
+    shared-memory tiles."""
+    from animatable_nerf_b200 import sample_utils, synthetic
+    verts, weights, _ = synthetic.make_body(seed=1)
+    g = torch.Generator().manual_seed(9)
+    v = torch.as_tensor(verts, dtype=torch.float32)[None]
+    w = torch.as_tensor(weights, dtype=torch.float32)[None]
+    assert v.shape == (1, 6890, 3) and w.shape == (1, 6890, 24)
+    lo, hi = v[0].min(0)[0] - 0.05, v[0].max(0)[0] + 0.05
+    pts = (torch.rand(1, 9011, 3, generator=g) * (hi - lo) + lo)
+    pts[0, :50] = v[0, 100:150]                                   # exactly on vertices
+
+    def oracle(p, vv, ww, K):
+        outs = [O.sample_blend_closest_points(p[:, i:i + 1024], vv, ww, K=K) for i in range(0, p.shape[1], 1024)]
+        return torch.cat([o[0] for o in outs], 1), torch.cat([o[1] for o in outs], 1)
+
+    for K in (5, 1):
+        ref_bw, ref_d = oracle(pts, v, w, K)
+        bw, d = sample_utils.sample_blend_closest_points(pts.to(dev), v.to(dev), w.to(dev), K=K)
+        assert bw.shape == ref_bw.shape and d.shape == ref_d.shape
+        assert float((bw.cpu() - ref_bw).abs().max()) <= 1e-5, K
+        assert float((d.cpu() - ref_d).abs().max()) <= 1e-5, K
+    big_v = torch.cat([v, v + 0.013, v[:, :1000] - 0.02], dim=1)          # 14 780 vertices: three tiles
+    big_w = torch.cat([w, w.flip(2), w[:, :1000]], dim=1)
+    ref_bw, ref_d = oracle(pts[:, :3000], big_v, big_w, 5)
+    bw, d = sample_utils.sample_blend_closest_points(pts[:, :3000].to(dev), big_v.to(dev), big_w.to(dev))
+    assert float((bw.cpu() - ref_bw).abs().max()) <= 1e-5 and float((d.cpu() - ref_d).abs().max()) <= 1e-5
