@@ -6,7 +6,7 @@ the host, as in the reference's Dataset (`lib/utils/if_nerf/if_nerf_data_utils.p
 :392-458 `batch_rodrigues` / `get_rigid_transformation`, :566-579 `get_bounds`;
 `lib/datasets/tpose_dataset.py`:148 `cv2.Rodrigues`).  Per-ray work (ray
 generation, box intersection) is NOT here: that runs on the GPU
-(`csrc/rays.cu`).
+(`csrc/geometry.cu`: `gen_rays_kernel`, `near_far_kernel`; host mirror `frontend.py`).
 """
 from __future__ import annotations
 

@@ -6,7 +6,9 @@ unchanged) and the same public methods with the same tensor shapes -- but every 
 sm_100a kernels of libaninerf_b200 through the C ABI.  There is no PyTorch fallback: tensors must be
 on a CUDA device.
 
-Backward is not part of this round: the methods run under `torch.no_grad()`.
+These methods are the inference entry points and run under `torch.no_grad()`; training (forward AND backward on the library's
+kernels, gradients for every parameter of this module) goes through `tpose_trainer.TrainStep` -- `Renderer.render` under
+`torch.enable_grad()` and `tpose_trainer.NetworkWrapper` -- not through these per-method calls.
 """
 from __future__ import annotations
 
