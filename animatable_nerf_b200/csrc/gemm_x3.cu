@@ -23,8 +23,8 @@
 namespace aninerf {
 
 constexpr int G_BM = 128;          // rows of the output tile = TMEM lanes
-constexpr int G_KC = 32;           // K elements per stage
-constexpr int G_STAGES = 3;
+constexpr int G_KC = 64;           // K elements per stage (12 MMAs per __syncthreads: the small products of a training step are latency-bound)
+constexpr int G_STAGES = 3;        // (2 for the 256-wide tile: 96 KB per stage)
 constexpr int G_THREADS = 256;
 
 struct GemmDev {
@@ -49,7 +49,9 @@ struct GemmSmem {
   static constexpr int A_STAGE = G_BM * G_KC * 2;       // bytes of one hi (or lo) plane
   static constexpr int B_STAGE = BN * G_KC * 2;
   static constexpr int STAGE = 2 * (A_STAGE + B_STAGE);
-  static constexpr int BYTES = G_STAGES * STAGE + 64;
+  static constexpr int STAGES = BN > 128 ? 2 : G_STAGES;
+  static constexpr int BYTES = STAGES * STAGE + 64;
+  static_assert(BYTES <= 232448, "shared memory budget");
 };
 
 // One K chunk of an operand -- rows [r0, r0+ROWS) x k [k0, k0+32) of X (zero outside [0,R) x [0,K)) -- in two steps, so that the
@@ -111,14 +113,15 @@ template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_constant__ GemmDev g) {
   using S = GemmSmem<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G_STAGES * S::STAGE);   // [0,STAGES): stage consumed; [STAGES]: accumulator complete
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + G_STAGES + 1);
+  constexpr int NS = S::STAGES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NS * S::STAGE);   // [0,STAGES): stage consumed; [STAGES]: accumulator complete
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NS + 1);
   const uint32_t bar0 = smem_u32(bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * G_BM, n0 = blockIdx.y * BN;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s <= G_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+    for (int s = 0; s <= NS; ++s) mbar_init(bar0 + 8 * s, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<1>(smem_u32(tmem_slot), BN < 32 ? 32 : BN);
@@ -150,9 +153,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_cons
   if (n_chunks > 0) load_chunk(0);
   int chunk = 0;
   for (; chunk < n_chunks; ++chunk) {
-    const int s = chunk % G_STAGES;
+    const int s = chunk % NS;
     const int seg = chunk < n0_chunks ? 0 : 1;
-    if (chunk >= G_STAGES) mbar_wait(bar0 + 8 * s, (uint32_t)((chunk / G_STAGES - 1) & 1), 20);   // MMAs of chunk - STAGES have read the stage
+    if (chunk >= NS) mbar_wait(bar0 + 8 * s, (uint32_t)((chunk / NS - 1) & 1), 20);   // MMAs of chunk - STAGES have read the stage
     uint8_t *base = smem + s * S::STAGE;
     uint8_t *a_hi = base, *a_lo = base + S::A_STAGE, *b_hi = base + 2 * S::A_STAGE, *b_lo = b_hi + S::B_STAGE;
     ra.store(a_hi, a_lo, g.a_rs[seg], g.a_ks[seg]);
@@ -175,9 +178,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_cons
       umma_commit<1>(bar0 + 8 * s);
     }
   }
-  if (threadIdx.x == 0) umma_commit<1>(bar0 + 8 * G_STAGES);   // arrives once every MMA above has retired
+  if (threadIdx.x == 0) umma_commit<1>(bar0 + 8 * NS);   // arrives once every MMA above has retired
   const bool any = chunk > 0;
-  if (any) mbar_wait(bar0 + 8 * G_STAGES, 0, 21);
+  if (any) mbar_wait(bar0 + 8 * NS, 0, 21);
   tc_fence_after();
 
   // ---- epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (= rows); warps w and w+4 split the columns --------------

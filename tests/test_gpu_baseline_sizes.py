@@ -227,3 +227,39 @@ def test_trained_like_nerf_field_margin(dev, precision):
     assert max(err.values()) <= RGB_TOL
     if precision == 3:
         assert max(err.values()) <= 2e-4 and sig_err <= 5e-4
+
+
+def test_config4_training_step_at_baseline_size(dev, frame_c2):
+    """BASELINE config 4 at its stated size: 1024 rays x 64 samples of the 1024x1024 frame (ray seed 3, colours seed 4, CPU-generator
+    jitter seed 5 -- SURVEY 8d), forward + backward through LBS + both blend-weight passes + NeRF + compositing: both losses within
+    1e-5 and every one of the 46 gradient tensors within 2e-3 (relative to the tensor's largest entry) of the oracle's autograd
+    (itself bit-equal to the reference trainer, oracle/VALIDATION.md)."""
+    from animatable_nerf_b200 import config
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_trainer import NetworkWrapper
+    frame, (K, R, T) = frame_c2
+    ro, rd, near, far, _ = O.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'])
+    tb, t_rand = synthetic.make_train_batch(frame, ro, rd, near, far, n_rays=1024, ray_seed=3, rgb_seed=4, jitter_seed=5)
+    assert tb['ray_o'].shape == (1, 1024, 3) and t_rand.shape == (1, 1024, 64)
+    sd = synthetic.make_state_dict(seed=0)
+    stats_o, grads_o = O.train_step_grads(sd, tb, O.OracleCfg(perturb=1.), t_rand=t_rand)
+    cfg = config.make_cfg(perturb=1.)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    w = NetworkWrapper(net.to(dev).train(), cfg)
+    with torch.enable_grad():
+        ret, loss, stats, _ = w(to_device(tb, dev), t_rand=t_rand)
+        loss.mean().backward()
+    torch.nn.utils.clip_grad_value_(w.net.parameters(), 40)
+    for k in ('bw_loss', 'img_loss', 'loss'):
+        assert abs(float(stats[k]) - stats_o[k]) <= 1e-5, (k, float(stats[k]), stats_o[k])
+    worst = ('', 0.0)
+    n = 0
+    for k, p in w.net.named_parameters():
+        ref = grads_o[k]
+        err = float((p.grad.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+        worst = max(worst, (k, err), key=lambda kv: kv[1])
+        assert err <= 2e-3, (k, err)
+        n += 1
+    assert n == 46
+    print('config 4 (1024 rays x 64): loss', float(loss), 'oracle', stats_o['loss'], 'worst gradient error', worst)
