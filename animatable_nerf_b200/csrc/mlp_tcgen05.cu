@@ -47,12 +47,15 @@ constexpr int KB_BYTES = TILE_M * 128;       // one K-block of the A tile: 128 r
 constexpr int PE_CHUNK0 = 0;                 // shared-memory A block 0 (chunks of 8 K elements 0..7): PE(xyz) 63 + pad
 constexpr int VIEW_CHUNK0 = 8;               // shared-memory A block 1 (chunks 8..15): PE(viewdir) 27 + pad (NeRF field)
 constexpr int KB_PE = 0, KB_HID0 = 1, KB_VIEW = 5;   // Step::a_kb: 0 PE(xyz) block, 1..4 hidden quarters (tensor memory), 5 PE(viewdir) block
-constexpr int STAGE_BYTES = 32768;          // ring stage: two K-blocks of a 256-wide layer (x1), or the hi + lo block of one (x3): the single
-                                             // MMA-issuing thread spends ~350 cycles per stage on waits / commits / decode whatever the stage holds
+// Ring stage.  The single MMA-issuing thread spends ~750 cycles per stage on commit / decode / `full` wait whatever the stage holds
+// (profiles/r02_mlp_trace.log), so a stage must carry MORE than that in MMA time: single pass: a whole 256-wide layer (four K-blocks,
+// 16 MMAs, 2.07 k cycles; with two K-blocks per stage the issue side was the bottleneck: 1.07 k of issue work per 1.03 k of MMAs);
+// split precision: the hi + lo block of one K-block (12 MMAs, 1.55 k cycles).
+constexpr int stage_bytes(int npass) { return npass == 1 ? 65536 : 32768; }
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_STEPS = 68;
 constexpr int SMEM_LIMIT = 232448;           // 227 KB
-constexpr int VIEW_LAYER_WRITE = 6;          // PE(viewdir) is written during this layer's epilogue (layer 5 was the last PE(xyz) reader)
+constexpr int VIEW_LAYER_WRITE = 1;          // PE(viewdir) (its own operand block) is written in the idle window before this layer's accumulator is ready
 
 struct Step {          // one weight-ring stage worth of MMAs: n_kb consecutive 64-wide K-blocks of the weight planes it holds
   uint32_t w_off;      // byte offset of this step's operand blocks in the packed buffer: [CTA0 half][CTA1 half]
@@ -117,7 +120,8 @@ struct MlpArgs {
 };
 
 // trace slots: 0 tile start, 1 PE done; per layer l base 8 + 16*l: +0 rows wait begin, +1 rows woke, +2 rows epilogue done
-// (arrived); +4 MMA waits a_ready, +5 MMA woke, +6 MMA issued the layer
+// (arrived), +7 rows published the first half of quarter 0, +3 MMA obtained it; +4 MMA starts the layer, +5 MMA has the layer's first weight stage, +6 MMA issued the layer; +8+q rows published
+// quarter q of the NEXT layer's operand; +12+q MMA obtained quarter q of THIS layer's operand
 #define ANI_TRACE(slot)                                                              \
   do {                                                                               \
     if (tracing) trace_base[(slot)] = (unsigned long long)clock64();                 \
@@ -229,7 +233,7 @@ constexpr int ROW_THREADS = ROW_WARPS * 32;        // 256
 // Threads of a CTA: the row (epilogue) threads, then one weight-producer warp and two warps for MMA issue / TMEM alloc / relays.
 constexpr int N_THREADS = ROW_THREADS + 96;
 constexpr int XCHG_BYTES = TILE_M * 4 * 4;         // per-row exchange between the two column halves
-constexpr int PROD_LANES = 8;                      // producer lanes take turns issuing the bulk copies: one thread keeps only
+constexpr int PROD_LANES = 8;                      // producer lanes share every stage's bulk copy: one thread keeps only
                                                    // ~one copy in flight (20-28 B/cycle, tools/bench_stream.cu); several
                                                    // threads overlap theirs (4 threads: 85-110 B/cycle)
 
@@ -246,6 +250,7 @@ struct Cfg {
   // whole 9 KB table resident the split-precision blend-weight field would have three ring stages instead of four)
   static constexpr int BIAS_BYTES = 256 * 4;
   static constexpr int FIXED = A_TOTAL + SCR_BYTES + HEAD_BYTES + XCHG + STEP_BYTES + BIAS_BYTES + 256;
+  static constexpr int STAGE_BYTES = stage_bytes(NPASS);
   static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
   static_assert(STAGES >= 2, "weight ring needs at least two stages");
@@ -276,18 +281,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   float *s_xchg = reinterpret_cast<float *>(smem + C::OFF_XCHG);
   Step *s_steps = reinterpret_cast<Step *>(smem + C::OFF_STEPS);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-  // barrier slots: [0,S) full, [S,2S) empty, [2S,2S+4) a_ready (leader CTA: one per K-block quarter of the hidden layer; every
-  // epilogue warp of BOTH CTAs arrives once per phase -- the peer's warps with a remote arrive, no relay), [2S+4] acc
+  // barrier slots: [0,S) full, [S,2S) empty, [2S,2S+5) a_ready (leader CTA: [q] = K-block quarter q of the hidden operand is
+  // written, [4] = the first half of quarter 0 is; every epilogue warp of BOTH CTAs arrives once per phase -- the peer's warps
+  // with a remote arrive, no relay), [2S+5] acc
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
   const uint32_t bar_a_ready = smem_u32(bars + 2 * C::STAGES);
-  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + 4);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 5);
-  static_assert((2 * C::STAGES + 6) * 8 <= 216, "barrier block overflow");
+  const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + 5);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 6);
+  static_assert((2 * C::STAGES + 7) * 8 <= 216, "barrier block overflow");
   // XT: cross-tile prefetch.  The next tile's input encoding is written into the PE(xyz) block right after the LAST layer's
   // accumulator barrier (the block is dead since layer 5), so the MMA issuer rolls from the last layer straight into the next
   // tile's layer 0 while the epilogue warps are still busy with this tile's head.
   constexpr bool XT = true;
+  // Quarter 0 of the hidden operand is published in two halves (split precision only: there the MMAs of half a quarter, 0.8 k cycles,
+  // cover the second half's conversion; in single-pass mode the epilogue is the critical path and the extra publish costs more than
+  // the earlier start gains: 32.7 k -> 35.0 k cycles per tile measured).
+  constexpr bool SPLIT_Q0 = NPASS == 3;
   constexpr int VCHUNK0 = VIEW_CHUNK0;
   float *s_grid = reinterpret_cast<float *>(smem + C::OFF_BAR + 224);   // lo[3], (dim-1)/ext [3] of the SMPL-weight volume
 
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       mbar_init(bar_full + 8 * s, (leader && PAIR == 2) ? 2 : 1);   // own bytes landed (+ the peer's relay on the leader)
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int q = 0; q < 4; ++q) mbar_init(bar_a_ready + 8 * q, ROW_WARPS * PAIR);   // one arrival per epilogue warp of the pair
+    for (int q = 0; q < 5; ++q) mbar_init(bar_a_ready + 8 * q, ROW_WARPS * PAIR);   // one arrival per epilogue warp of the pair
     mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
@@ -334,24 +344,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   if (warp == RW) {
     // ===== weight producer: this CTA's half of every operand block ==============================
     if (lane < PROD_LANES) {
-      uint32_t stage = 0, phase = 0, turn = 0;
+      uint32_t stage = 0, phase = 0;
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
         for (int l = 0; l < n_layers; ++l) {
           for (int s = F.layers[l].step0; s < F.layers[l].step0 + F.layers[l].n_steps; ++s) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);               // all producer lanes stay in step (no divergent spin)
-            if (turn == (uint32_t)lane) {
-              const Step ps = s_steps[s];
-              const uint32_t bytes = (uint32_t)(F.layers[l].n_pad / PAIR) * 128u * ps.n_kb *
-                                     (((ps.flags & STEP_HI) ? 1u : 0u) + ((ps.flags & STEP_LO) ? 1u : 0u));   // this CTA's half of the stage
-              if (args.debug & 1) {
-                mbar_arrive(bar_full + 8 * stage);
-              } else {
-                mbar_expect_tx(bar_full + 8 * stage, bytes);
-                bulk_g2s(smem_u32(ring + stage * STAGE_BYTES), F.image + ps.w_off + cta_rank * bytes, bytes, bar_full + 8 * stage);
-              }
+            const Step ps = s_steps[s];
+            const uint32_t bytes = (uint32_t)(F.layers[l].n_pad / PAIR) * 128u * ps.n_kb *
+                                   (((ps.flags & STEP_HI) ? 1u : 0u) + ((ps.flags & STEP_LO) ? 1u : 0u));   // this CTA's half of the stage
+            // lane 0 announces the stage's bytes, then every lane copies one eighth of it: one thread keeps only about one bulk copy
+            // in flight, eight overlap theirs (every stage size is a multiple of 8 x 1 KB)
+            if (lane == 0) {
+              if (args.debug & 1) mbar_arrive(bar_full + 8 * stage);
+              else mbar_expect_tx(bar_full + 8 * stage, bytes);
             }
             __syncwarp((1u << PROD_LANES) - 1u);
-            turn = (turn + 1) % PROD_LANES;
+            if (!(args.debug & 1)) {
+              const uint32_t part = bytes / PROD_LANES;
+              bulk_g2s(smem_u32(ring + stage * C::STAGE_BYTES) + lane * part, F.image + ps.w_off + cta_rank * bytes + lane * part, part,
+                       bar_full + 8 * stage);
+            }
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     }
   } else if (warp > RW) {
     const int role = warp - (RW + 1);
-    if (leader && role == 0 && lane == 0) {
+    if (leader && role == 0 && elect_one()) {
       // ===== MMA issuer (leader CTA): ONE thread.  Everything it does between two MMAs is on the critical path of the tensor pipe
       // (tools/bench_mma.cu: a few dozen dependent scalar instructions per MMA already halve the rate), so the loop is kept to:
       // per ring stage one decode + one `full` wait + one commit; per K-block one descriptor per operand and (first touch of a
@@ -385,8 +397,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           // barriers complete together and are all consumed up front (never after the commit: the epilogue's arrivals for layer 1
           // must not overtake).  The accumulator buffer was drained two layers ago.
           int next_q = 0;
-          if (l == 0)
+          bool got_first = false;                                 // a_ready[4]: the first half of quarter 0
+          if (l == 0) {
             for (; next_q < 4; ++next_q) mbar_wait(bar_a_ready + 8 * next_q, a_phase, 2 + next_q);
+            if (SPLIT_Q0) mbar_wait(bar_a_ready + 8 * 4, a_phase, 6);
+            got_first = true;
+          }
           uint32_t fresh = 0u;
           for (int s = s0; s < s0 + n_layer_steps; ++s) {
             const Step st = s_steps[s];
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             mbar_wait(bar_full + 8 * stage, full_phase, 3);   // TMA-written operands: CTA-scope acquire is enough for the async proxy
             tc_fence_after();
             if (s == s0) ANI_TRACE(8 + 16 * l + 5);
-            uint32_t b_blk = ring_u32 + stage * STAGE_BYTES;
+            uint32_t b_blk = ring_u32 + stage * (uint32_t)C::STAGE_BYTES;
             for (int kb = 0; kb < (int)st.n_kb; ++kb, b_blk += per_kb) {
               const int akb = (int)st.a_kb + kb;
               const bool hidden = akb >= KB_HID0 && akb < KB_HID0 + 4;
@@ -403,30 +419,52 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               const uint64_t bdl = smem_desc_sw128(b_blk + (hi_stage ? blk : 0u));
               if (hidden) {
                 // A from tensor memory: quarter q of the PREVIOUS layer's accumulator buffer, re-quantised in place by its epilogue.
-                // Slice k (16 K elements): the thread that owns columns [64q + 32 (k/2), +32) wrote the hi pairs at the start of its
-                // range and (split precision) the lo pairs 16 columns further.
+                // Slice k (16 K elements) comes from 16 fp32 columns [64q + 16k, +16): their owner wrote the hi pairs over the first 8
+                // of them and (split precision) the lo pairs over the other 8.  Quarter 0 is published in two halves -- slices
+                // {0, 2} (the first 16 columns of each of the row's two threads), then {1, 3} -- so that the layer starts as early
+                // as possible: the window between the previous layer's last MMA and this layer's first one is tensor-pipe idle time.
                 const int q = akb - KB_HID0;
-                for (; next_q <= q; ++next_q) {
-                  mbar_wait(bar_a_ready + 8 * next_q, a_phase, 2 + next_q);   // (CTA-scope acquire: a cluster-scope one invalidates the L1)
-                  tc_fence_after();
-                }
                 const uint32_t ta = a_prev + (uint32_t)q * 64u;
-                if (hi_stage) {
+                auto issue_slices = [&](int kfirst, int kstep) {
+                  if (hi_stage) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint32_t tk = ta + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
-                    umma_bf16_ts<PAIR>(acc, tk, bdh + (uint64_t)(2 * k), idesc, k == 0 ? fresh : 1u);
-                    if (NPASS == 3) umma_bf16_ts<PAIR>(acc, tk + 16u, bdh + (uint64_t)(2 * k), idesc, 1u);
+                    for (int k = kfirst; k < 4; k += kstep) {
+                      const uint32_t tk = ta + (uint32_t)(k * 16);
+                      umma_bf16_ts<PAIR>(acc, tk, bdh + (uint64_t)(2 * k), idesc, fresh);
+                      fresh = 1u;
+                      if (NPASS == 3) umma_bf16_ts<PAIR>(acc, tk + 8u, bdh + (uint64_t)(2 * k), idesc, 1u);
+                    }
                   }
-                  fresh = 1u;
-                }
-                if (lo_stage) {
+                  if (lo_stage) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint32_t tk = ta + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
-                    umma_bf16_ts<PAIR>(acc, tk, bdl + (uint64_t)(2 * k), idesc, k == 0 ? fresh : 1u);
+                    for (int k = kfirst; k < 4; k += kstep) {
+                      umma_bf16_ts<PAIR>(acc, ta + (uint32_t)(k * 16), bdl + (uint64_t)(2 * k), idesc, fresh);
+                      fresh = 1u;
+                    }
                   }
-                  fresh = 1u;
+                };
+                if (SPLIT_Q0 && q == 0) {
+                  if (!got_first) {
+                    mbar_wait(bar_a_ready + 8 * 4, a_phase, 6);        // (CTA-scope acquire: a cluster-scope one invalidates the L1)
+                    tc_fence_after();
+                    got_first = true;
+                    ANI_TRACE(8 + 16 * l + 3);
+                  }
+                  issue_slices(0, 2);
+                  if (next_q == 0) {
+                    mbar_wait(bar_a_ready, a_phase, 2);
+                    tc_fence_after();
+                    ANI_TRACE(8 + 16 * l + 12);
+                    next_q = 1;
+                  }
+                  issue_slices(1, 2);
+                } else {
+                  for (; next_q <= q; ++next_q) {
+                    mbar_wait(bar_a_ready + 8 * next_q, a_phase, 2 + next_q);
+                    tc_fence_after();
+                    ANI_TRACE(8 + 16 * l + 12 + next_q);
+                  }
+                  issue_slices(0, 1);
                 }
               } else {
                 // the input encodings: shared-memory operand blocks (ready since the tile's start / the previous layers)
@@ -461,6 +499,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           }
           ANI_TRACE(8 + 16 * l + 6);
           for (; next_q < 4; ++next_q) mbar_wait(bar_a_ready + 8 * next_q, a_phase, 7);   // keep every quarter's phase in step
+          if (SPLIT_Q0 && !got_first) mbar_wait(bar_a_ready + 8 * 4, a_phase, 7);
           a_phase ^= 1;
         }
       }
@@ -530,7 +569,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         else write_pe<NPASS, 10, 4, 8>(a_hi, a_lo, PE_CHUNK0, row, px, py, pz);
         fence_proxy_async();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) arrive_warp(q);   // the input encoding readies every quarter's barrier for layer 0
+        for (int q = 0; q < (SPLIT_Q0 ? 5 : 4); ++q) arrive_warp(q);   // the input encoding readies every quarter's barrier for layer 0
       }
       ANI_TRACE(1);
 
@@ -591,6 +630,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           }
           if (l == 7) ANI_TRACE(5);
         }
+        if (NERF && l == VIEW_LAYER_WRITE && !args.density_only) {
+          // PE(viewdir) -> its own operand block, while this layer's MMAs run.  Its last reader was the PREVIOUS tile's view layer,
+          // complete since that tile's last accumulator barrier; its next reader is issued after this tile's later publishes.
+          float vx = 0.f, vy = 0.f, vz = 0.f;
+          if (valid) {
+            vx = __ldg(args.viewdir + 3 * gi);
+            vy = __ldg(args.viewdir + 3 * gi + 1);
+            vz = __ldg(args.viewdir + 3 * gi + 2);
+          }
+          if (half == 0) write_pe<NPASS, 4, 0, 2>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
+          else write_pe<NPASS, 4, 2, 4>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
+          fence_proxy_async();           // (shared-memory operand: visible to the tensor core before the next publishes)
+        }
         ANI_TRACE(8 + 16 * l);
         mbar_wait(bar_acc, acc_phase, 5 + 100 * l);
         acc_phase ^= 1;
@@ -612,59 +664,51 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             else write_pe<NPASS, 10, 4, 8>(a_hi, a_lo, PE_CHUNK0, row, nx, ny, nz);
             fence_proxy_async();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) arrive_warp(q);
+            for (int q = 0; q < (SPLIT_Q0 ? 5 : 4); ++q) arrive_warp(q);
           }
         }
         ANI_TRACE(8 + 16 * l + 1);
         const bool alpha_layer = NERF && l == 7;             // the trunk's last layer: alpha_fc is an fp32 dot in its epilogue
         if (!last) {
-          if (NERF && l == VIEW_LAYER_WRITE) {
-            // layer 5 was the last reader of PE(xyz); PE(viewdir) goes to its own K-block (or, split precision, over PE(xyz))
-            float vx = 0.f, vy = 0.f, vz = 0.f;
-            if (valid) {
-              vx = __ldg(args.viewdir + 3 * gi);
-              vy = __ldg(args.viewdir + 3 * gi + 1);
-              vz = __ldg(args.viewdir + 3 * gi + 2);
-            }
-            if (half == 0) write_pe<NPASS, 4, 0, 2>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
-            else write_pe<NPASS, 4, 2, 4>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
-            fence_proxy_async();           // (shared-memory operand: visible to the tensor core before this layer's publishes)
-          }
-          // hidden layer: bias + ReLU -> bf16 pairs (hi / lo) -> written with tcgen05.st over the accumulator columns just read, one
-          // 64-column quarter (= one K-block of the next layer) at a time; this thread: 32 of the quarter's columns [c, c+32):
-          // hi pairs -> columns [c, c+16), lo pairs (split precision) -> [c+16, c+32).  Software-pipelined: the TMEM load of
-          // quarter q+1 is in flight while quarter q is converted, stored and published.
+          // hidden layer: bias + ReLU -> bf16 pairs (hi / lo) -> written with tcgen05.st over the accumulator columns just read.
+          // This thread owns 32 of every quarter's 64 columns; each run of 16 fp32 columns [c, c+16) (= one K=16 slice of the next
+          // layer's operand) becomes hi pairs in [c, c+8) and (split precision) lo pairs in [c+8, c+16).  Quarters are published
+          // one at a time (= one K-block of the next layer), quarter 0 in two halves; software-pipelined: the TMEM load of the
+          // next columns is in flight while the current ones are converted, stored and published.
           uint32_t va[32], vb[32];
-          auto process = [&](const uint32_t (&v)[32], int q) {
-            const int col0 = q * 64 + half * 32;               // first output column of this thread's group
-            uint32_t hi[16], lo[16];
+          // signal barrier b (0..3: quarter b complete; 4: first half of quarter 0) once every store issued so far has landed
+          auto publish = [&](int b) {
+            tmem_st_wait();
+            tc_fence_before();
+            arrive_warp(b);
+            ANI_TRACE(8 + 16 * l + (b < 4 ? 8 + b : 7));
+          };
+          // (measured, kept out: publishing a run only after the NEXT run's conversion, to cover the store latency, made the first
+          // publish of a layer 200 cycles later and the whole tile 1-2 % slower)
+          auto process16 = [&](const uint32_t (&v)[32], int off, int q, int publish_after) {
+            const int col0 = q * 64 + half * 32 + off;         // first fp32 column of the run
+            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
+            for (int j4 = 0; j4 < 2; ++j4) {
               const float4 b0 = *reinterpret_cast<const float4 *>(bias + col0 + j4 * 8);
               const float4 b1 = *reinterpret_cast<const float4 *>(bias + col0 + j4 * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float x[8];
               if (NPASS == 1 && !alpha_layer) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j4 * 8 + j]) + bb[j];
+                for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[off + j4 * 8 + j]) + bb[j];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hi[j4 * 4 + j] = pack_bf16_relu(x[2 * j], x[2 * j + 1]);      // the ReLU rides on the conversion
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[j4 * 8 + j]) + bb[j], 0.f);
+                for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[off + j4 * 8 + j]) + bb[j], 0.f);
                 if (alpha_layer) {
                   const float4 w0 = *reinterpret_cast<const float4 *>(s_head + col0 + j4 * 8);
                   const float4 w1 = *reinterpret_cast<const float4 *>(s_head + col0 + j4 * 8 + 4);
-                  float sg = sigma;
-                  sg = fmaf(x[0], w0.x, sg);
-                  sg = fmaf(x[1], w0.y, sg);
-                  sg = fmaf(x[2], w0.z, sg);
-                  sg = fmaf(x[3], w0.w, sg);
-                  sg = fmaf(x[4], w1.x, sg);
-                  sg = fmaf(x[5], w1.y, sg);
-                  sg = fmaf(x[6], w1.z, sg);
-                  sg = fmaf(x[7], w1.w, sg);
-                  sigma = sg;
+                  // (four independent chains: one dependent chain of 128 FMAs per layer is 0.5 k cycles of latency on the publish path)
+                  const float p0 = fmaf(x[2], w0.z, x[0] * w0.x), p1 = fmaf(x[3], w0.w, x[1] * w0.y);
+                  const float p2 = fmaf(x[6], w1.z, x[4] * w1.x), p3 = fmaf(x[7], w1.w, x[5] * w1.y);
+                  sigma += (p0 + p1) + (p2 + p3);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -674,32 +718,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               }
             }
             if (!(args.debug & 2)) {
-              tmem_st16(t_acc + col0, hi);
-              if (NPASS == 3) tmem_st16(t_acc + col0 + 16, lo);
+              tmem_st8(t_acc + col0, hi);
+              if (NPASS == 3) tmem_st8(t_acc + col0 + 8, lo);
             }
+            if (publish_after >= 0) publish(publish_after);
           };
-          // publish the K-block written so far
-          auto publish = [&](int q) {
-            tmem_st_wait();
-            tc_fence_before();
-            arrive_warp(q);
-          };
-          tmem_ld32(t_acc + half * 32, va);
+          // (publish_after: 0..3: quarter complete with this run; 4: first half of quarter 0; -1: nothing)
+          if (SPLIT_Q0) {
+            tmem_ld16<0>(t_acc + half * 32, va);
+            tmem_ld_wait();
+            tmem_ld16<16>(t_acc + half * 32 + 16, va);
+            process16(va, 0, 0, 4);
+          } else {
+            tmem_ld32(t_acc + half * 32, va);
+            tmem_ld_wait();
+            process16(va, 0, 0, -1);
+          }
           tmem_ld_wait();
           tmem_ld32(t_acc + 64 + half * 32, vb);
-          process(va, 0);
-          publish(0);
+          process16(va, 16, 0, 0);
           tmem_ld_wait();
           tmem_ld32(t_acc + 128 + half * 32, va);
-          process(vb, 1);
-          publish(1);
+          process16(vb, 0, 1, -1);
+          process16(vb, 16, 1, 1);
           tmem_ld_wait();
           tmem_ld32(t_acc + 192 + half * 32, vb);
-          process(va, 2);
-          publish(2);
+          process16(va, 0, 2, -1);
+          process16(va, 16, 2, 2);
           tmem_ld_wait();
-          process(vb, 3);
-          if (alpha_layer && half == 1) xchg[row * 4] = sigma;   // read by the row's other thread after the next acc barrier
+          process16(vb, 0, 3, -1);
+          process16(vb, 16, 3, -1);
+          if (alpha_layer && half == 1) xchg[row * 4] = sigma;   // read by the row's other thread after the next acc barrier (ordered by the publish)
           publish(3);
           ANI_TRACE(8 + 16 * l + 2);
         } else if (!NERF) {
@@ -778,7 +827,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             tmem_ld_wait();
             const int col0 = q * 64 + half * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sg = fmaf(fmaxf(__uint_as_float(v[j]) + bias[col0 + j], 0.f), s_head[col0 + j], sg);
+            for (int j = 0; j < 32; j += 8) {            // same association as the full path's layer-7 epilogue
+              float x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[j + i]) + bias[col0 + j + i], 0.f);
+              const float *w = s_head + col0 + j;
+              const float p0 = fmaf(x[2], w[2], x[0] * w[0]), p1 = fmaf(x[3], w[3], x[1] * w[1]);
+              const float p2 = fmaf(x[6], w[6], x[4] * w[4]), p3 = fmaf(x[7], w[7], x[5] * w[5]);
+              sg += (p0 + p1) + (p2 + p3);
+            }
           }
           tc_fence_before();
           if (half == 1) xchg[row * 4] = sg;
@@ -926,15 +983,16 @@ static int describe_layers(int field, const aninerf_layer *L, int n_layers, std:
     h.relu = L[l].relu;
     h.n_tables = L[l].n_tables;
     int want_k, want_n;
-    // (hidden K-blocks first wherever a layer also reads an encoding: the MMA issuer then never waits on more than the next quarter)
+    // (the ENCODING's K-block first wherever a layer also reads one: those MMAs need nothing from the previous layer's epilogue, so
+    // they run in the window between its accumulator barrier and its first published quarter, when the tensor pipe is otherwise idle)
     if (l == 0) {
       want_k = 63; want_n = 256; h.segs = {{0, 63, 0, 4}};
     } else if (l == 5) {     // skip layer: [PE(xyz), hidden]
-      want_k = 63 + 256; want_n = 256; h.segs = {{63, 256, 1, 4}, {0, 63, 0, 4}};
+      want_k = 63 + 256; want_n = 256; h.segs = {{0, 63, 0, 4}, {63, 256, 1, 4}};
     } else if (l < 8) {
       want_k = 256; want_n = 256; h.segs = {{0, 256, 1, 4}};
     } else if (nerf) {       // folded view layer: [hidden, PE(viewdir)]; PE(viewdir) K-block: see VIEW_CHUNK0
-      want_k = 256 + 27; want_n = 128; h.segs = {{0, 256, 1, 4}, {256, 27, -1, 2}};
+      want_k = 256 + 27; want_n = 128; h.segs = {{256, 27, -1, 2}, {0, 256, 1, 4}};
     } else {
       want_k = 256; want_n = ANINERF_N_BONES; h.segs = {{0, 256, 1, 4}};
     }
@@ -956,7 +1014,7 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
     const HostLayer &h = H[l];
     const int n_half = h.n_pad / kPair;                     // weight rows held by each CTA of the pair
     const size_t blk = (size_t)n_half * 128;                // one SWIZZLE_128B K-block (64 K elements) of one CTA's rows, one plane
-    const int cap = (int)(STAGE_BYTES / blk);               // plane-blocks per ring stage
+    const int cap = (int)(stage_bytes(npass) / blk);               // plane-blocks per ring stage
     // A stage holds whole K-blocks with all their planes when they fit (narrow layers: the 24-wide head of the blend-weight field is
     // ONE stage), else one plane of one K-block (256-wide layers in split precision: the hi and the lo block travel separately)
     const bool split_planes = cap < planes;
@@ -975,7 +1033,7 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
           const size_t cta_bytes = blk * (size_t)(p1 - p0) * nkb;
           s.w_off = (uint32_t)image.size();
           const uint32_t step_bytes = (uint32_t)(cta_bytes * kPair);
-          if (cta_bytes > (size_t)STAGE_BYTES || (cta_bytes & 1023u)) return fail(ANINERF_EINVAL, "%s: internal: bad step size%s", __func__);
+          if (cta_bytes > (size_t)stage_bytes(npass) || (cta_bytes & 1023u)) return fail(ANINERF_EINVAL, "%s: internal: bad step size%s", __func__);
           s.a_kb = (uint8_t)(a_kb0 + kb0);
           s.n_kb = (uint8_t)nkb;
           s.k16_last = (uint8_t)(kb0 + nkb == n_kb ? sg.k16_last : 4);

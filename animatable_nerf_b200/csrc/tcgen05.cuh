@@ -183,6 +183,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// 16 of the 32 destination registers (v[OFF .. OFF+16)) <- 16 consecutive columns
+template <int OFF>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[OFF + 0]), "=r"(v[OFF + 1]), "=r"(v[OFF + 2]), "=r"(v[OFF + 3]), "=r"(v[OFF + 4]), "=r"(v[OFF + 5]), "=r"(v[OFF + 6]),
+        "=r"(v[OFF + 7]), "=r"(v[OFF + 8]), "=r"(v[OFF + 9]), "=r"(v[OFF + 10]), "=r"(v[OFF + 11]), "=r"(v[OFF + 12]), "=r"(v[OFF + 13]),
+        "=r"(v[OFF + 14]), "=r"(v[OFF + 15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B contiguous;

@@ -170,13 +170,13 @@ def print_trace(name, t):
     t0 = t[0]
     say(f'{name}: tile start 0, PE done {t[1] - t0}, smpl gather {t[4] - t0}..{t[5] - t0}, tile done {t[3] - t0}')
     for l in range(9):
-        for ts in range(2):
-            b = 8 + 16 * l + 8 * ts
-            if t[b + 5] == 0:
-                continue
-            say(f'  L{l} slot{ts}: mma wait_a {t[b + 4] - t0} woke {t[b + 5] - t0} issued {t[b + 6] - t0} | rows wait {t[b] - t0} '
-                f'woke {t[b + 1] - t0} done {t[b + 2] - t0 if t[b + 2] else 0}  || issue {t[b + 6] - t[b + 5]} '
-                f'epilogue {t[b + 2] - t[b + 1] if t[b + 2] else 0}')
+        b = 8 + 16 * l
+        if t[b + 5] == 0:
+            continue
+        rel = lambda x: int(x - t0) if x else 0
+        say(f'  L{l}: mma start {rel(t[b + 4])} first stage {rel(t[b + 5])} got half {rel(t[b + 3])} quarters {[rel(x) for x in t[b + 12:b + 16]]} '
+            f'issued {rel(t[b + 6])} | rows wait {rel(t[b])} woke {rel(t[b + 1])} published half {rel(t[b + 7])} quarters '
+            f'{[rel(x) for x in t[b + 8:b + 12]]} done {rel(t[b + 2])}')
 
 
 def trace_frame():
