@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -537,6 +538,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     };
     uint8_t *a_hi = smem + C::OFF_A_HI, *a_lo = smem + C::OFF_A_LO;
     uint32_t acc_phase = 0, lc = 0;
+    const bool debug_no_st = (args.debug & 2) != 0;
     bool pe_ready = false;                       // XT: this tile's encoding was written during the previous tile's last layer
     int64_t ngi = 0;
     bool nvalid = false;
@@ -669,7 +671,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         }
         ANI_TRACE(8 + 16 * l + 1);
         const bool alpha_layer = NERF && l == 7;             // the trunk's last layer: alpha_fc is an fp32 dot in its epilogue
-        if (!last) {
+        // (the alpha variant is a separate instantiation of the epilogue: as a run-time branch inside every 8-column group it cost
+        // a BSSY / BSYNC pair, a not-taken jump over ~35 instructions and instruction-fetch stalls per group -- ncu: `no_inst`,
+        // `branch_resolving` on the publish path of the single-pass NeRF field)
+        auto hidden_epilogue = [&](auto alpha_tag) {
+          constexpr bool ALPHA = decltype(alpha_tag)::value;
           // hidden layer: bias + ReLU -> bf16 pairs (hi / lo) -> written with tcgen05.st over the accumulator columns just read.
           // This thread owns 32 of every quarter's 64 columns; each run of 16 fp32 columns [c, c+16) (= one K=16 slice of the next
           // layer's operand) becomes hi pairs in [c, c+8) and (split precision) lo pairs in [c+8, c+16).  Quarters are published
@@ -694,7 +700,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               const float4 b1 = *reinterpret_cast<const float4 *>(bias + col0 + j4 * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float x[8];
-              if (NPASS == 1 && !alpha_layer) {
+              if (NPASS == 1 && !ALPHA) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[off + j4 * 8 + j]) + bb[j];
 #pragma unroll
@@ -702,7 +708,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = fmaxf(__uint_as_float(v[off + j4 * 8 + j]) + bb[j], 0.f);
-                if (alpha_layer) {
+                if (ALPHA) {
                   const float4 w0 = *reinterpret_cast<const float4 *>(s_head + col0 + j4 * 8);
                   const float4 w1 = *reinterpret_cast<const float4 *>(s_head + col0 + j4 * 8 + 4);
                   // (four independent chains: one dependent chain of 128 FMAs per layer is 0.5 k cycles of latency on the publish path)
@@ -717,7 +723,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                 }
               }
             }
-            if (!(args.debug & 2)) {
+            if (!debug_no_st) {
               tmem_st8(t_acc + col0, hi);
               if (NPASS == 3) tmem_st8(t_acc + col0 + 8, lo);
             }
@@ -748,9 +754,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           tmem_ld_wait();
           process16(vb, 0, 3, -1);
           process16(vb, 16, 3, -1);
-          if (alpha_layer && half == 1) xchg[row * 4] = sigma;   // read by the row's other thread after the next acc barrier (ordered by the publish)
+          if (ALPHA && half == 1) xchg[row * 4] = sigma;   // read by the row's other thread after the next acc barrier (ordered by the publish)
           publish(3);
           ANI_TRACE(8 + 16 * l + 2);
+        };
+        if (!last) {
+          if constexpr (NERF) {
+            if (alpha_layer) hidden_epilogue(std::true_type{});
+            else hidden_epilogue(std::false_type{});
+          } else {
+            hidden_epilogue(std::false_type{});
+          }
         } else if (!NERF) {
           // ---- blend-weight head: softmax(log(smpl_bw + 1e-9) + delta), fused inverse LBS --------
           // The row's two threads take 12 bones each and meet three times (max, sum, skinning matrix) through a scratch

@@ -242,7 +242,8 @@ def test_config4_training_step_at_baseline_size(dev, frame_c2):
     tb, t_rand = synthetic.make_train_batch(frame, ro, rd, near, far, n_rays=1024, ray_seed=3, rgb_seed=4, jitter_seed=5)
     assert tb['ray_o'].shape == (1, 1024, 3) and t_rand.shape == (1, 1024, 64)
     sd = synthetic.make_state_dict(seed=0)
-    stats_o, grads_o = O.train_step_grads(sd, tb, O.OracleCfg(perturb=1.), t_rand=t_rand)
+    with torch.enable_grad():                 # (this module's tests otherwise run under no_grad, as evaluation does)
+        stats_o, grads_o = O.train_step_grads(sd, tb, O.OracleCfg(perturb=1.), t_rand=t_rand)
     cfg = config.make_cfg(perturb=1.)
     net = Network(cfg)
     net.load_state_dict(sd)
