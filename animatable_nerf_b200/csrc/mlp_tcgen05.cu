@@ -48,11 +48,14 @@ constexpr int KB_BYTES = TILE_M * 128;       // one K-block of the A tile: 128 r
 constexpr int PE_CHUNK0 = 0;                 // shared-memory A block 0 (chunks of 8 K elements 0..7): PE(xyz) 63 + pad
 constexpr int VIEW_CHUNK0 = 8;               // shared-memory A block 1 (chunks 8..15): PE(viewdir) 27 + pad (NeRF field)
 constexpr int KB_PE = 0, KB_HID0 = 1, KB_VIEW = 5;   // Step::a_kb: 0 PE(xyz) block, 1..4 hidden quarters (tensor memory), 5 PE(viewdir) block
-// Ring stage.  The single MMA-issuing thread spends ~750 cycles per stage on commit / decode / `full` wait whatever the stage holds
-// (profiles/r02_mlp_trace.log), so a stage must carry MORE than that in MMA time: single pass: a whole 256-wide layer (four K-blocks,
-// 16 MMAs, 2.07 k cycles; with two K-blocks per stage the issue side was the bottleneck: 1.07 k of issue work per 1.03 k of MMAs);
-// split precision: the hi + lo block of one K-block (12 MMAs, 1.55 k cycles).
+// Ring stage.  Every stage boundary costs the MMA-issuing thread a commit, a decode and a `full` wait, during which the tensor pipe
+// drains unless enough MMAs are queued (profiles/r02_mlp_trace.log: ~350 cycles of pipe idle time per boundary with 8 MMAs per stage).
+// Single pass: a stage is a whole 256-wide layer (four K-blocks, 16 MMAs, 2.07 k cycles); only two such stages fit, so the small
+// weight blocks of the input encodings (PE(xyz) in layers 0 and 5, PE(viewdir) in the view layer: 8-16 KB) travel through their
+// own AUXILIARY slot instead of taking a ring stage each (they did at first: the 64 KB stage behind them then arrived ~1 k cycles
+// late, twice per tile).  Split precision: a stage is the hi + lo block of one K-block (12 MMAs, 1.55 k cycles), four stages.
 constexpr int stage_bytes(int npass) { return npass == 1 ? 65536 : 32768; }
+constexpr int aux_bytes(int npass) { return npass == 1 ? 16384 : 0; }
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_STEPS = 68;
 constexpr int SMEM_LIMIT = 232448;           // 227 KB
@@ -66,9 +69,10 @@ struct Step {          // one weight-ring stage worth of MMAs: n_kb consecutive 
   uint8_t flags;       // 1: first step of its layer: fresh accumulator; 2: last step of its layer: commit the acc barrier;
                        // 4: the stage holds the HIGH weight plane: passes x_hi * w_hi (+ x_lo * w_hi in split precision);
                        // 8: the stage holds the LOW weight plane (split precision): pass x_hi * w_lo
+                       // 16: the step's (small) operand block travels through the AUXILIARY slot, not through the ring
 };
 static_assert(sizeof(Step) == 8, "Step is packed into 8 bytes: the table lives in shared memory");
-enum { STEP_FIRST = 1, STEP_LAST = 2, STEP_HI = 4, STEP_LO = 8 };
+enum { STEP_FIRST = 1, STEP_LAST = 2, STEP_HI = 4, STEP_LO = 8, STEP_AUX = 16 };
 
 struct LayerDev {
   int32_t n_pad;       // MMA N (multiple of 32)
@@ -250,7 +254,8 @@ struct Cfg {
   // (one layer's bias at a time, staged by the row threads in the idle window before the layer's accumulator is ready: with the
   // whole 9 KB table resident the split-precision blend-weight field would have three ring stages instead of four)
   static constexpr int BIAS_BYTES = 256 * 4;
-  static constexpr int FIXED = A_TOTAL + SCR_BYTES + HEAD_BYTES + XCHG + STEP_BYTES + BIAS_BYTES + 256;
+  static constexpr int AUX_BYTES = aux_bytes(NPASS);
+  static constexpr int FIXED = A_TOTAL + AUX_BYTES + SCR_BYTES + HEAD_BYTES + XCHG + STEP_BYTES + BIAS_BYTES + 256;
   static constexpr int STAGE_BYTES = stage_bytes(NPASS);
   static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
@@ -260,7 +265,8 @@ struct Cfg {
   static constexpr int OFF_A_HI = 0;
   static constexpr int OFF_A_LO = A_PLANE;                      // only when NPASS == 3
   static constexpr int OFF_RING = A_TOTAL;
-  static constexpr int OFF_SCR = OFF_RING + STAGES * STAGE_BYTES;
+  static constexpr int OFF_AUX = OFF_RING + STAGES * STAGE_BYTES;
+  static constexpr int OFF_SCR = OFF_AUX + AUX_BYTES;
   static constexpr int OFF_HEAD = OFF_SCR + SCR_BYTES;
   static constexpr int OFF_XCHG = OFF_HEAD + HEAD_BYTES;
   static constexpr int OFF_STEPS = OFF_XCHG + XCHG;
@@ -290,7 +296,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   const uint32_t bar_a_ready = smem_u32(bars + 2 * C::STAGES);
   const uint32_t bar_acc = smem_u32(bars + 2 * C::STAGES + 5);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 6);
-  static_assert((2 * C::STAGES + 7) * 8 <= 216, "barrier block overflow");
+  const uint32_t bar_aux_full = smem_u32(bars + 2 * C::STAGES + 7), bar_aux_empty = smem_u32(bars + 2 * C::STAGES + 8);
+  static_assert((2 * C::STAGES + 9) * 8 <= 216, "barrier block overflow");
   // XT: cross-tile prefetch.  The next tile's input encoding is written into the PE(xyz) block right after the LAST layer's
   // accumulator barrier (the block is dead since layer 5), so the MMA issuer rolls from the last layer straight into the next
   // tile's layer 0 while the epilogue warps are still busy with this tile's head.
@@ -331,6 +338,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       mbar_init(bar_full + 8 * s, (leader && PAIR == 2) ? 2 : 1);   // own bytes landed (+ the peer's relay on the leader)
       mbar_init(bar_empty + 8 * s, 1);
     }
+    mbar_init(bar_aux_full, (leader && PAIR == 2) ? 2 : 1);
+    mbar_init(bar_aux_empty, 1);
     for (int q = 0; q < 5; ++q) mbar_init(bar_a_ready + 8 * q, ROW_WARPS * PAIR);   // one arrival per epilogue warp of the pair
     mbar_init(bar_acc, 1);
     fence_barrier_init();
@@ -345,27 +354,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   if (warp == RW) {
     // ===== weight producer: this CTA's half of every operand block ==============================
     if (lane < PROD_LANES) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, aux_phase = 0;
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
+        const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && lane == 0;
+        unsigned long long *const trace_base = args.trace;
         for (int l = 0; l < n_layers; ++l) {
           for (int s = F.layers[l].step0; s < F.layers[l].step0 + F.layers[l].n_steps; ++s) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);               // all producer lanes stay in step (no divergent spin)
             const Step ps = s_steps[s];
+            const bool aux = C::AUX_BYTES > 0 && (ps.flags & STEP_AUX) != 0;
+            const uint32_t fb = aux ? bar_aux_full : bar_full + 8 * stage, eb = aux ? bar_aux_empty : bar_empty + 8 * stage;
+            const uint32_t dst = aux ? smem_u32(smem + C::OFF_AUX) : smem_u32(ring + stage * C::STAGE_BYTES);
+            mbar_wait(eb, (aux ? aux_phase : phase) ^ 1, 1);               // all producer lanes stay in step (no divergent spin)
+            if (s < 16) ANI_TRACE(416 + 2 * s);                            // slots 416 + 2 s: the step's slot is free; + 1: its copies are issued
             const uint32_t bytes = (uint32_t)(F.layers[l].n_pad / PAIR) * 128u * ps.n_kb *
                                    (((ps.flags & STEP_HI) ? 1u : 0u) + ((ps.flags & STEP_LO) ? 1u : 0u));   // this CTA's half of the stage
             // lane 0 announces the stage's bytes, then every lane copies one eighth of it: one thread keeps only about one bulk copy
             // in flight, eight overlap theirs (every stage size is a multiple of 8 x 1 KB)
             if (lane == 0) {
-              if (args.debug & 1) mbar_arrive(bar_full + 8 * stage);
-              else mbar_expect_tx(bar_full + 8 * stage, bytes);
+              if (args.debug & 1) mbar_arrive(fb);
+              else mbar_expect_tx(fb, bytes);
             }
             __syncwarp((1u << PROD_LANES) - 1u);
             if (!(args.debug & 1)) {
               const uint32_t part = bytes / PROD_LANES;
-              bulk_g2s(smem_u32(ring + stage * C::STAGE_BYTES) + lane * part, F.image + ps.w_off + cta_rank * bytes + lane * part, part,
-                       bar_full + 8 * stage);
+              bulk_g2s(dst + lane * part, F.image + ps.w_off + cta_rank * bytes + lane * part, part, fb);
             }
-            if (++stage == C::STAGES) {
+            if (s < 16) ANI_TRACE(416 + 2 * s + 1);
+            if (aux) {
+              aux_phase ^= 1;
+            } else if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
             }
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       // (tools/bench_mma.cu: a few dozen dependent scalar instructions per MMA already halve the rate), so the loop is kept to:
       // per ring stage one decode + one `full` wait + one commit; per K-block one descriptor per operand and (first touch of a
       // quarter) one a_ready wait; per K=16 slice a constant +32 bytes / +8 columns. ====================================
-      uint32_t stage = 0, full_phase = 0, a_phase = 0, lc = 0;      // ring position; lc: running layer count (accumulator buffer)
+      uint32_t stage = 0, full_phase = 0, aux_phase = 0, a_phase = 0, lc = 0;   // ring position; lc: running layer count (accumulator buffer)
       const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI), a_lo = smem_u32(smem + C::OFF_A_LO);
       const uint32_t ring_u32 = smem_u32(ring);
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
@@ -409,10 +426,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             const Step st = s_steps[s];
             const bool hi_stage = (st.flags & STEP_HI) != 0, lo_stage = NPASS == 3 && (st.flags & STEP_LO) != 0;
             const uint32_t per_kb = blk * ((hi_stage ? 1u : 0u) + (lo_stage ? 1u : 0u));
-            mbar_wait(bar_full + 8 * stage, full_phase, 3);   // TMA-written operands: CTA-scope acquire is enough for the async proxy
+            const bool aux = C::AUX_BYTES > 0 && (st.flags & STEP_AUX) != 0;          // a small encoding block in the auxiliary slot
+            // (TMA-written operands: CTA-scope acquire is enough for the async proxy)
+            mbar_wait(aux ? bar_aux_full : bar_full + 8 * stage, aux ? aux_phase : full_phase, 3);
             tc_fence_after();
             if (s == s0) ANI_TRACE(8 + 16 * l + 5);
-            uint32_t b_blk = ring_u32 + stage * (uint32_t)C::STAGE_BYTES;
+            if (s < 16) ANI_TRACE(448 + s);                                  // slots 448 + s: the issuer has the step's operands
+            uint32_t b_blk = aux ? smem_u32(smem + C::OFF_AUX) : ring_u32 + stage * (uint32_t)C::STAGE_BYTES;
             for (int kb = 0; kb < (int)st.n_kb; ++kb, b_blk += per_kb) {
               const int akb = (int)st.a_kb + kb;
               const bool hidden = akb >= KB_HID0 && akb < KB_HID0 + 4;
@@ -491,9 +511,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                 }
               }
             }
-            umma_commit<PAIR>(bar_empty + 8 * stage);            // frees the ring stage (both CTAs) once these MMAs retire
+            umma_commit<PAIR>(aux ? bar_aux_empty : bar_empty + 8 * stage);   // frees the slot (both CTAs) once these MMAs retire
             if (st.flags & STEP_LAST) umma_commit<PAIR>(bar_acc);   // layer done: its accumulator is ready
-            if (++stage == C::STAGES) {
+            if (aux) {
+              aux_phase ^= 1u;
+            } else if (++stage == C::STAGES) {
               stage = 0;
               full_phase ^= 1u;
             }
@@ -506,17 +528,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       }
     } else if (lane == 0 && PAIR == 2 && !leader && role == 0) {
       // ===== relay (peer CTA): tell the leader when this CTA's half of a stage has landed ========
-      uint32_t stage = 0, phase = 0;
-      const uint32_t full_leader = mapa_u32(bar_full, 0);
-      int64_t total = 0;
-      for (int l = 0; l < n_layers; ++l) total += F.layers[l].n_steps;
+      uint32_t stage = 0, phase = 0, aux_phase = 0;
+      const uint32_t full_leader = mapa_u32(bar_full, 0), aux_full_leader = mapa_u32(bar_aux_full, 0);
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-        for (int64_t s = 0; s < total; ++s) {
-          mbar_wait(bar_full + 8 * stage, phase, 4);
-          mbar_arrive_remote(full_leader + 8 * stage);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
+        for (int l = 0; l < n_layers; ++l) {
+          for (int s = F.layers[l].step0; s < F.layers[l].step0 + F.layers[l].n_steps; ++s) {
+            if (C::AUX_BYTES > 0 && (s_steps[s].flags & STEP_AUX)) {
+              mbar_wait(bar_aux_full, aux_phase, 4);
+              mbar_arrive_remote(aux_full_leader);
+              aux_phase ^= 1;
+            } else {
+              mbar_wait(bar_full + 8 * stage, phase, 4);
+              mbar_arrive_remote(full_leader + 8 * stage);
+              if (++stage == C::STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
           }
         }
       }
@@ -1054,6 +1082,8 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
           const bool first = si == 0 && kb0 == 0 && part == 0;
           const bool last = si + 1 == h.segs.size() && kb0 + nkb == n_kb && part + 1 == (split_planes ? planes : 1);
           s.flags = (uint8_t)((first ? STEP_FIRST : 0) | (last ? STEP_LAST : 0) | (p0 == 0 ? STEP_HI : 0) | (p1 == 2 ? STEP_LO : 0));
+          // single pass: the small blocks of the input encodings go through the auxiliary slot (see stage_bytes)
+          if (npass == 1 && (a_kb0 == KB_PE || a_kb0 == KB_VIEW) && cta_bytes <= (size_t)aux_bytes(npass)) s.flags |= STEP_AUX;
           image.resize(image.size() + step_bytes, 0);
           for (int r = 0; r < kPair; ++r)             // image = [CTA0 rows][CTA1 rows]; per K-block: [hi plane][lo plane]
             for (int kb = 0; kb < nkb; ++kb)

@@ -204,9 +204,8 @@ def trace_frame():
         _lib.lib().aninerf_debug_set_trace(None)
         t = buf.cpu().numpy()
         print_trace(name, t)
-        st = t[320:448].reshape(16, 8)
-        say(f'{name} layer-2 issue timeline per step (top, a_ready ok, full ok, issued; relative to tile start): ' +
-            ' | '.join(f'{int(r[0] - t[0])} {int(r[1] - r[0])} {int(r[2] - r[1])} {int(r[3] - r[2])}' for r in st if r[0]))
+        say(f'{name} weight steps (slot free, copies issued -> issuer has it; relative to tile start): ' + ' | '.join(
+            f's{i}: {int(t[416 + 2 * i] - t[0])} {int(t[417 + 2 * i] - t[0])} -> {int(t[448 + i] - t[0])}' for i in range(16) if t[448 + i]))
         tp = t[256:]
         say(f'{name} PEER CTA rows (own clock, relative to its tile start): ' + ' | '.join(
             f'L{l} woke {tp[8 + 16 * l + 1] - tp[0]} done {tp[8 + 16 * l + 2] - tp[0] if tp[8 + 16 * l + 2] else 0}' for l in range(9)))
