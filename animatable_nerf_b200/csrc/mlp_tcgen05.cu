@@ -129,7 +129,7 @@ struct MlpArgs {
 // quarter q of the NEXT layer's operand; +12+q MMA obtained quarter q of THIS layer's operand
 #define ANI_TRACE(slot)                                                              \
   do {                                                                               \
-    if (tracing) trace_base[(slot)] = (unsigned long long)clock64();                 \
+    if (TRACE && tracing) trace_base[(slot)] = (unsigned long long)clock64();        \
   } while (0)
 
 // write 8 consecutive K elements of `row` (one 16-byte chunk) into A chunk `chunk` (K-block chunk / 8, SWIZZLE_128B);
@@ -277,7 +277,9 @@ struct Cfg {
   static_assert(OFF_RING % 1024 == 0, "ring stages must be 1024-byte aligned");
 };
 
-template <int NPASS, bool NERF, int PAIR>
+// TRACE: the clock64 timeline of tools/gpu_diag.py.  A separate instantiation: the predicated stamps alone cost 1.5 % (split precision)
+// to 2.2 % (single pass) of the tile time when compiled in (A/B on one GPU: 61.0 k -> 60.1 k, 29.6 k -> 29.0 k cycles per tile).
+template <int NPASS, bool NERF, int PAIR, bool TRACE>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant__ MlpArgs args) {
   constexpr int RW = ROW_WARPS;                      // row (epilogue) warps; warp RW: producer; RW+1, RW+2: MMA issue / relays
   using C = Cfg<NPASS, NERF>;
@@ -356,8 +358,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     if (lane < PROD_LANES) {
       uint32_t stage = 0, phase = 0, aux_phase = 0;
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-        const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units && lane == 0;
-        unsigned long long *const trace_base = args.trace;
         for (int l = 0; l < n_layers; ++l) {
           for (int s = F.layers[l].step0; s < F.layers[l].step0 + F.layers[l].n_steps; ++s) {
             const Step ps = s_steps[s];
@@ -365,7 +365,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             const uint32_t fb = aux ? bar_aux_full : bar_full + 8 * stage, eb = aux ? bar_aux_empty : bar_empty + 8 * stage;
             const uint32_t dst = aux ? smem_u32(smem + C::OFF_AUX) : smem_u32(ring + stage * C::STAGE_BYTES);
             mbar_wait(eb, (aux ? aux_phase : phase) ^ 1, 1);               // all producer lanes stay in step (no divergent spin)
-            if (s < 16) ANI_TRACE(416 + 2 * s);                            // slots 416 + 2 s: the step's slot is free; + 1: its copies are issued
             const uint32_t bytes = (uint32_t)(F.layers[l].n_pad / PAIR) * 128u * ps.n_kb *
                                    (((ps.flags & STEP_HI) ? 1u : 0u) + ((ps.flags & STEP_LO) ? 1u : 0u));   // this CTA's half of the stage
             // lane 0 announces the stage's bytes, then every lane copies one eighth of it: one thread keeps only about one bulk copy
@@ -379,7 +378,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               const uint32_t part = bytes / PROD_LANES;
               bulk_g2s(dst + lane * part, F.image + ps.w_off + cta_rank * bytes + lane * part, part, fb);
             }
-            if (s < 16) ANI_TRACE(416 + 2 * s + 1);
             if (aux) {
               aux_phase ^= 1;
             } else if (++stage == C::STAGES) {
@@ -401,7 +399,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
       const uint32_t a_hi = smem_u32(smem + C::OFF_A_HI), a_lo = smem_u32(smem + C::OFF_A_LO);
       const uint32_t ring_u32 = smem_u32(ring);
       for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-        const bool tracing = args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units;
+        const bool tracing = TRACE && args.trace && blockIdx.x == 0 && ut == (int64_t)args.trace_iter * n_units;
         unsigned long long *const trace_base = args.trace;
         for (int l = 0; l < n_layers; ++l, ++lc) {
           const int n_pad = F.layers[l].n_pad;
@@ -431,7 +429,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             mbar_wait(aux ? bar_aux_full : bar_full + 8 * stage, aux ? aux_phase : full_phase, 3);
             tc_fence_after();
             if (s == s0) ANI_TRACE(8 + 16 * l + 5);
-            if (s < 16) ANI_TRACE(448 + s);                                  // slots 448 + s: the issuer has the step's operands
             uint32_t b_blk = aux ? smem_u32(smem + C::OFF_AUX) : ring_u32 + stage * (uint32_t)C::STAGE_BYTES;
             for (int kb = 0; kb < (int)st.n_kb; ++kb, b_blk += per_kb) {
               const int akb = (int)st.a_kb + kb;
@@ -567,14 +564,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
     uint8_t *a_hi = smem + C::OFF_A_HI, *a_lo = smem + C::OFF_A_LO;
     uint32_t acc_phase = 0, lc = 0;
     const bool debug_no_st = (args.debug & 2) != 0;
+    auto load_bias = [&](int l) {                        // this thread's entry of layer l's bias row (latent-code tables: row `latent`)
+      const int rt = (int)threadIdx.x;
+      const float *gb = F.bias + F.layers[l].bias_off + min(max(latent, 0), F.layers[l].n_tables - 1) * F.layers[l].n_out;
+      return rt < F.layers[l].n_out ? __ldg(gb + rt) : 0.f;
+    };
+    float bias_next = load_bias(0);
     bool pe_ready = false;                       // XT: this tile's encoding was written during the previous tile's last layer
     int64_t ngi = 0;
     bool nvalid = false;
     float nx = 0.f, ny = 0.f, nz = 0.f;
     for (int64_t ut = unit; ut < n_utiles; ut += n_units) {
-      const bool tracing = args.trace && blockIdx.x < 2 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
+      const bool tracing = TRACE && args.trace && blockIdx.x < 2 && ut == (int64_t)args.trace_iter * n_units && threadIdx.x == 0;
       unsigned long long *const trace_base = args.trace + (blockIdx.x == 1 ? 256 : 0);     // the peer CTA of cluster 0: slots 256.. (its own clock)
-      if (args.trace && blockIdx.x == 0 && threadIdx.x == 0 && ut / n_units < 90) args.trace[160 + ut / n_units] = (unsigned long long)clock64();
+      if (TRACE && args.trace && blockIdx.x == 0 && threadIdx.x == 0 && ut / n_units < 90) args.trace[160 + ut / n_units] = (unsigned long long)clock64();
       int64_t gi;
       bool valid;
       float px, py, pz, sigma = 0.f;
@@ -607,30 +610,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         const bool last = l == n_layers - 1;
         const int n_pad = F.layers[l].n_pad;
         {
-          // this layer's bias row -> shared memory (the previous layer's readers are done: first barrier)
-          const int rt = (int)threadIdx.x;                     // row threads are threads 0..255
-          const float *gb = F.bias + F.layers[l].bias_off + min(max(latent, 0), F.layers[l].n_tables - 1) * F.layers[l].n_out;
-          const float bv = rt < F.layers[l].n_out ? __ldg(gb + rt) : 0.f;
+          // this layer's bias row (fetched after the previous layer's last publish) -> shared memory (the previous layer's readers
+          // are done: first barrier)
           asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
-          s_bias[rt] = bv;
+          s_bias[threadIdx.x] = bias_next;                     // row threads are threads 0..255
           asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
         }
         const float *bias = s_bias;
         float *xchg = s_xchg;                                // exchange between the row's two threads (NeRF field)
         const uint32_t t_acc = t_lane + (lc & 1u) * 256u;
-        if (!NERF && l < 8) {
-          // Initial SMPL weights of this row (this thread: bones 12*half .. +11): ONE trilinear corner per layer, fetched in
-          // the idle window before the layer's accumulator is ready and accumulated in registers (ATen's corner order).
-          // The whole gather is 98 KB per tile from L2, which also feeds the 1 MB weight stream: done in one burst it ran at
-          // the L2 bandwidth roof for 7-8k cycles and delayed the layer it shared the window with; 12 KB per window hides.
-          if (l == 0) {
+        if (!NERF && l >= 1) {
+          // Initial SMPL weights of this row (this thread: bones 12*half .. +11): ONE trilinear corner per layer (corner l-1 in the
+          // window of layer l = 1..8), fetched in the idle window before the layer's accumulator is ready and accumulated in
+          // registers (ATen's corner order).  The whole gather is 98 KB per tile from L2, which also feeds the 1 MB weight stream:
+          // done in one burst it ran at the L2 bandwidth roof for 7-8k cycles and delayed the layer it shared the window with;
+          // 12 KB per window hides.  Not in layer 0's window: with the cross-tile prefetch that layer's MMAs are done before the
+          // tile starts, and the gather's L2 latency (~2 k cycles) sat on the critical path.
+          if (l == 1) {
             ANI_TRACE(4);
 #pragma unroll
             for (int k = 0; k < ANINERF_N_BONES / 2; ++k) smpl[k] = 0.f;
           }
           if (valid) {
             if (args.smpl_bw) {
-              if (l == 7) {
+              if (l == 8) {
                 const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi * ANINERF_N_BONES) + half * 3;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             } else {
               float wc;
               int oc;
-              fast_corner(s_grid, args.grid_dim, px, py, pz, l, wc, oc);
+              fast_corner(s_grid, args.grid_dim, px, py, pz, l - 1, wc, oc);
               const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)oc * ANINERF_N_BONES) + half * 3;
               float4 c4[3];
 #pragma unroll
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
               }
             }
           }
-          if (l == 7) ANI_TRACE(5);
+          if (l == 8) ANI_TRACE(5);
         }
         if (NERF && l == VIEW_LAYER_WRITE && !args.density_only) {
           // PE(viewdir) -> its own operand block, while this layer's MMAs run.  Its last reader was the PREVIOUS tile's view layer,
@@ -698,6 +701,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           }
         }
         ANI_TRACE(8 + 16 * l + 1);
+        if (last) bias_next = load_bias(0);                    // the next tile's first layer (in flight during the head)
         const bool alpha_layer = NERF && l == 7;             // the trunk's last layer: alpha_fc is an fp32 dot in its epilogue
         // (the alpha variant is a separate instantiation of the epilogue: as a run-time branch inside every 8-column group it cost
         // a BSSY / BSYNC pair, a not-taken jump over ~35 instructions and instruction-fetch stalls per group -- ncu: `no_inst`,
@@ -785,6 +789,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           if (ALPHA && half == 1) xchg[row * 4] = sigma;   // read by the row's other thread after the next acc barrier (ordered by the publish)
           publish(3);
           ANI_TRACE(8 + 16 * l + 2);
+          bias_next = load_bias(l + 1);                        // (off the publish path; consumed at the next layer's start)
         };
         if (!last) {
           if constexpr (NERF) {
@@ -1116,12 +1121,13 @@ static int build_image(const aninerf_layer *L, const std::vector<HostLayer> &H, 
   return ANINERF_OK;
 }
 
-template <int NPASS, bool NERF>
+template <int NPASS, bool NERF, bool TRACE = false>
 static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
   using C = Cfg<NPASS, NERF>;
+  if (!TRACE && a.trace) return launch_mlp<NPASS, NERF, true>(a, st);      // diagnostics build of the same kernel
   static bool configured = false;
   if (!configured) {
-    ANI_CUDA(cudaFuncSetAttribute(mlp_kernel<NPASS, NERF, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    ANI_CUDA(cudaFuncSetAttribute(mlp_kernel<NPASS, NERF, kPair, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   const int64_t rows_per_unit = (int64_t)TILE_M * kPair;
@@ -1140,7 +1146,7 @@ static int launch_mlp(const MlpArgs &a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ANI_CUDA(cudaLaunchKernelEx(&cfg, mlp_kernel<NPASS, NERF, kPair>, a));
+  ANI_CUDA(cudaLaunchKernelEx(&cfg, mlp_kernel<NPASS, NERF, kPair, TRACE>, a));
   ANI_LAUNCHED();
   return ANINERF_OK;
 }

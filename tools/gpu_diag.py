@@ -211,6 +211,41 @@ def trace_frame():
             f'L{l} woke {tp[8 + 16 * l + 1] - tp[0]} done {tp[8 + 16 * l + 2] - tp[0] if tp[8 + 16 * l + 2] else 0}' for l in range(9)))
 
 
+def mlp_time():
+    """Device time of the two MLP kernels inside the bench frame (the library's stage events), no tracing: for A/B comparisons of
+    two builds of the library on ONE box (tools/ab.sh)."""
+    import ctypes as C
+    import bench
+    from animatable_nerf_b200 import frontend
+    frame, cam, sd = bench.build_workload(1024)
+    K, R, T = cam
+    ray_o, ray_d, near, far, mask = frontend.get_rays_within_bounds(1024, 1024, K, R, T, frame['wbounds'], device=dev)
+    cfg = config.make_cfg(perturb=0., b200_render_only=True)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    r = Renderer(net.to(dev).eval(), cfg)
+    batch = synthetic.make_render_batch(frame, ray_o, ray_d, near, far, device=dev)
+    L = _lib.lib()
+    for _ in range(5):
+        r.render_device(batch, want_bw=False)
+    torch.cuda.synchronize()
+    ms_buf, calls_buf = (C.c_double * 9)(), (C.c_int64 * 9)()
+    L.aninerf_profile_read(ms_buf, calls_buf, 1)
+    L.aninerf_profile_enable(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(40):
+        r.render_device(batch, want_bw=False)
+    b.record()
+    torch.cuda.synchronize()
+    L.aninerf_profile_enable(0)
+    L.aninerf_profile_read(ms_buf, calls_buf, 1)
+    st = {name: ms_buf[i] / max(1, calls_buf[i]) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
+    say(f"mlp_time: frame {a.elapsed_time(b) / 40:.4f} ms | bw_field_posed {st.get('bw_field_posed', 0):.4f} ms | nerf_field {st.get('nerf_field', 0):.4f} ms")
+
+
+if 'mlp_time' in sys.argv[1:]:
+    section('mlp_time', mlp_time)
 if 'trace' in sys.argv[1:]:
     section('trace', trace)
 if 'trace_frame' in sys.argv[1:]:
