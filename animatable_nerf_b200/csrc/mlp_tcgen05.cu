@@ -59,6 +59,7 @@ constexpr int aux_bytes(int npass) { return npass == 1 ? 16384 : 0; }
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_STEPS = 68;
 constexpr int SMEM_LIMIT = 232448;           // 227 KB
+constexpr int XT_LAYER = 6;                  // the next tile's PE(xyz) is written in the idle window before this layer's accumulator is ready
 constexpr int VIEW_LAYER_WRITE = 1;          // PE(viewdir) (its own operand block) is written in the idle window before this layer's accumulator is ready
 
 struct Step {          // one weight-ring stage worth of MMAs: n_kb consecutive 64-wide K-blocks of the weight planes it holds
@@ -300,9 +301,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 6);
   const uint32_t bar_aux_full = smem_u32(bars + 2 * C::STAGES + 7), bar_aux_empty = smem_u32(bars + 2 * C::STAGES + 8);
   static_assert((2 * C::STAGES + 9) * 8 <= 216, "barrier block overflow");
-  // XT: cross-tile prefetch.  The next tile's input encoding is written into the PE(xyz) block right after the LAST layer's
-  // accumulator barrier (the block is dead since layer 5), so the MMA issuer rolls from the last layer straight into the next
-  // tile's layer 0 while the epilogue warps are still busy with this tile's head.
+  // XT: cross-tile prefetch.  The next tile's input encoding is written into the PE(xyz) block (dead since layer 5) in layer
+  // XT_LAYER's idle window and published right after the LAST layer's accumulator barrier, so the MMA issuer rolls from the last
+  // layer straight into the next tile's layer 0 while the epilogue warps are still busy with this tile's head.
   constexpr bool XT = true;
   // Quarter 0 of the hidden operand is published in two halves (split precision only: there the MMAs of half a quarter, 0.8 k cycles,
   // cover the second half's conversion; in single-pass mode the epilogue is the critical path and the extra publish costs more than
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                   }
                   issue_slices(0, 1);
                 }
+
               } else {
                 // the input encodings: shared-memory operand blocks (ready since the tile's start / the previous layers)
                 const bool full4 = !(kb + 1 == (int)st.n_kb && st.k16_last == 2);
@@ -676,13 +678,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           else write_pe<NPASS, 4, 2, 4>(a_hi, a_lo, VCHUNK0, row, vx, vy, vz);
           fence_proxy_async();           // (shared-memory operand: visible to the tensor core before the next publishes)
         }
-        ANI_TRACE(8 + 16 * l);
-        mbar_wait(bar_acc, acc_phase, 5 + 100 * l);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (XT && last) {
-          // The next tile's input encoding.  It must come AFTER this layer's accumulator barrier: an mbarrier arrival is not tagged
-          // with a phase, and only the completed MMAs of the last layer prove that every thread's arrivals on a_ready[] for it are in.
+        if (XT && l == XT_LAYER) {
+          // The NEXT tile's input encoding -> the PE(xyz) block, in the idle window of this layer: the block's last reader (the skip
+          // layer 5) completed before this thread passed that layer's accumulator barrier.  (Written after the LAST layer's barrier,
+          // as at first, its ~1.8 k cycles sat on the tile's critical path: barrier -> encoding -> head -> next tile's epilogue.)
           pe_ready = ut + n_units < n_utiles;
           if (pe_ready) {
             ngi = ((ut + n_units) * PAIR + cta_rank) * TILE_M + row;
@@ -696,9 +695,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
             if (half == 0) write_pe<NPASS, 10, 0, 4>(a_hi, a_lo, PE_CHUNK0, row, nx, ny, nz);
             else write_pe<NPASS, 10, 4, 8>(a_hi, a_lo, PE_CHUNK0, row, nx, ny, nz);
             fence_proxy_async();
-#pragma unroll
-            for (int q = 0; q < (SPLIT_Q0 ? 5 : 4); ++q) arrive_warp(q);
           }
+        }
+        ANI_TRACE(8 + 16 * l);
+        mbar_wait(bar_acc, acc_phase, 5 + 100 * l);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (XT && last && pe_ready) {
+          // The next tile's input encoding (written in layer XT_LAYER's window) is PUBLISHED here.  That must come AFTER this layer's
+          // accumulator barrier: an mbarrier arrival is not tagged with a phase, and only the completed MMAs of the last layer prove
+          // that every thread's arrivals on a_ready[] for it are in.
+#pragma unroll
+          for (int q = 0; q < (SPLIT_Q0 ? 5 : 4); ++q) arrive_warp(q);
         }
         ANI_TRACE(8 + 16 * l + 1);
         if (last) bias_next = load_bias(0);                    // the next tile's first layer (in flight during the head)

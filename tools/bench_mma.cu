@@ -141,7 +141,16 @@ constexpr int B_BYTES = 128 * 256 * 2;      // up to N/2 = 128 rows per CTA x K=
 
 // mma_test: thread (warp 8, lane 0) of the leader issues `n_mma` MMAs of the given shape back to back (K walks over 16 slices of a
 // K=256 operand, repeatedly), commits, waits.  Warps 0..side_warps-1 run the side traffic until the MMAs are done.
-template <int PAIR>
+// ELECT: the issuing thread is chosen with elect.sync (ptxas then knows the region is executed by ONE thread and issues UTCHMMA
+// straight from uniform registers); without it (`lane == 0`) every MMA sits in a compiler-generated ELECT / BRA.U.ANY waterfall
+// loop behind R2UR moves, and the ISSUE costs ~105 cycles per MMA -- which is what limited every N < 256 shape in the first
+// version of this benchmark, and the single-pass field of the MLP kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <int PAIR, bool ELECT>
 __global__ void __launch_bounds__(320, 1) mma_kernel(int src, int n, int n_mma, int side, int side_warps, Result *res) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sA = smem;                          // 64 KB
@@ -184,27 +193,33 @@ __global__ void __launch_bounds__(320, 1) mma_kernel(int src, int n, int n_mma, 
   long long t0 = 0, t1 = 0;
   bool ok = true;
   if (warp == 8) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && (ELECT ? elect_one() : lane == 0)) {
       const uint32_t idesc = instr_desc(n, 128 * PAIR);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       const int nb = n / PAIR;                                  // B rows held by each CTA
-      const int commit_every = g_commit_every, wait_every = g_wait_every;
+      const int commit_every = g_commit_every, wait_every = g_wait_every;      // (in MMAs; multiples of 16)
+      const uint64_t ad_sw = desc_sw128(a0), bd_sw = desc_sw128(b0);
+      const uint64_t ad_n = desc_none(a0, 2048, 128), bd_n = desc_none(b0, nb * 16, 128);
+      const uint32_t b_kb = (uint32_t)(nb * 128) >> 4, b_k16 = (uint32_t)(2 * nb * 16) >> 4;      // descriptor address units (16 B)
       t0 = clock64();
-      for (int i = 0; i < n_mma; ++i) {
-        const int k = i & 15;                                   // K=16 slice of the K=256 operand
-        uint64_t bd;
-        if (src == SRC_SS_SW128) bd = desc_sw128(b0 + (k >> 2) * (nb * 128) + (k & 3) * 32);
-        else bd = desc_none(b0 + k * 2 * (nb * 16), nb * 16, 128);
-        if (wait_every > 0 && (i & (wait_every - 1)) == 0) (void)mbar_try_wait(smem_u32(&bars[2]), 1);       // (powers of two: no division in the issue loop)
+      // sixteen K=16 slices per pass, every descriptor a constant offset from a loop-invariant base: the issue loop of the MLP kernel
+      for (int i = 0; i < n_mma; i += 16) {
+        if (wait_every > 0 && (i & (wait_every - 1)) == 0) (void)mbar_try_wait(smem_u32(&bars[2]), 1);
         if (src == SRC_TS) {
-          umma_ts<PAIR>(tmem, tmem + 256 + k * 8, bd, idesc, i ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_ts<PAIR>(tmem, tmem + 256 + k * 8, bd_sw + (uint64_t)((k >> 2) * b_kb + (k & 3) * 2), idesc, (i | k) ? 1u : 0u);
+        } else if (src == SRC_SS_SW128) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_ss<PAIR>(tmem, ad_sw + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), bd_sw + (uint64_t)((k >> 2) * b_kb + (k & 3) * 2), idesc,
+                          (i | k) ? 1u : 0u);
         } else {
-          uint64_t ad;
-          if (src == SRC_SS_SW128) ad = desc_sw128(a0 + (k >> 2) * (128 * 128) + (k & 3) * 32);
-          else ad = desc_none(a0 + k * 2 * 2048, 2048, 128);
-          umma_ss<PAIR>(tmem, ad, bd, idesc, i ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_ss<PAIR>(tmem, ad_n + (uint64_t)(k * 256), bd_n + (uint64_t)(k * b_k16), idesc, (i | k) ? 1u : 0u);
         }
-        if (commit_every > 0 && (i & (commit_every - 1)) == commit_every - 1) umma_commit<PAIR>(smem_u32(&bars[1]));
+        if (commit_every > 0 && ((i + 16) & (commit_every - 1)) == 0) umma_commit<PAIR>(smem_u32(&bars[1]));
       }
       umma_commit<PAIR>(smem_u32(&bars[0]));
       const long long t_issued = clock64();
@@ -512,10 +527,10 @@ static void run_verify() {
     }
 }
 
-template <int PAIR>
+template <int PAIR, bool ELECT = true>
 static void run_mma(const char *name, int src, int n, int n_mma, int side, int side_warps, int clusters, Result *d_res) {
   const int smem = A_BYTES + B_BYTES + 65536;
-  CK(cudaFuncSetAttribute(mma_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(mma_kernel<PAIR, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * PAIR);
   cfg.blockDim = dim3(320);
@@ -529,7 +544,7 @@ static void run_mma(const char *name, int src, int n, int n_mma, int side, int s
   cfg.numAttrs = 1;
   CK(cudaMemset(d_res, 0, sizeof(Result) * 256));
   for (int rep = 0; rep < 2; ++rep) {          // second run = warm
-    CK(cudaLaunchKernelEx(&cfg, mma_kernel<PAIR>, src, n, n_mma, side, side_warps, d_res));
+    CK(cudaLaunchKernelEx(&cfg, mma_kernel<PAIR, ELECT>, src, n, n_mma, side, side_warps, d_res));
     CK(cudaDeviceSynchronize());
   }
   Result h[256];
@@ -560,9 +575,9 @@ int main(int argc, char **argv) {
   run_verify();
   const int NM = 256;
   const char *srcs[3] = {"A smem SWIZZLE_NONE", "A smem SWIZZLE_128B", "A in TMEM (.ts)"};
-  printf("## 1. MMA rate, nothing else running (aux = cycles to ISSUE the %d MMAs)\n", NM);
+  printf("## 1. MMA rate, nothing else running, issued by an ELECTED lane (aux = cycles to ISSUE the %d MMAs)\n", NM);
   for (int src = 0; src < 3; ++src)
-    for (int n : {256, 128, 64}) {
+    for (int n : {256, 128, 64, 32}) {
       char name[96];
       snprintf(name, sizeof(name), "cta_group::2 M=256, %s", srcs[src]);
       run_mma<2>(name, src, n, NM, SIDE_NONE, 0, clusters, d_res);
@@ -573,8 +588,15 @@ int main(int argc, char **argv) {
       snprintf(name, sizeof(name), "cta_group::1 M=128, %s", srcs[src]);
       run_mma<1>(name, src, n, NM, SIDE_NONE, 0, clusters, d_res);
     }
+  printf("## 1a. the same issued by `lane == 0` of a divergent warp (compiler-generated waterfall loop around every MMA)\n");
+  for (int src : {1, 2})
+    for (int n : {256, 128, 32}) {
+      char name[96];
+      snprintf(name, sizeof(name), "lane==0: cta_group::2 M=256, %s", srcs[src]);
+      run_mma<2, false>(name, src, n, NM, SIDE_NONE, 0, clusters, d_res);
+    }
   printf("## 1b. the same with a tcgen05.commit (and an mbarrier try_wait by the issuing thread) every n MMAs, as a weight ring does per stage\n");
-  for (int every : {0, 4, 8, 64}) {
+  for (int every : {0, 16, 64}) {
     CK(cudaMemcpyToSymbol(g_commit_every, &every, sizeof(int)));
     for (int w : {0, 1}) {
       const int we = w ? every : 0;
