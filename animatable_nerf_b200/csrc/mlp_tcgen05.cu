@@ -622,9 +622,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
         float *xchg = s_xchg;                                // exchange between the row's two threads (NeRF field)
         const uint32_t t_acc = t_lane + (lc & 1u) * 256u;
         if (!NERF && l >= 1) {
-          // Initial SMPL weights of this row (this thread: bones 12*half .. +11): ONE trilinear corner per layer (corner l-1 in the
-          // window of layer l = 1..8), fetched in the idle window before the layer's accumulator is ready and accumulated in
-          // registers (ATen's corner order).  The whole gather is 98 KB per tile from L2, which also feeds the 1 MB weight stream:
+          // Initial SMPL weights of this row (this thread: bones 12*half .. +11): ONE trilinear corner per layer (two in layer 1's
+          // window), fetched in the idle window before the layer's accumulator is ready and accumulated in registers (ATen's
+          // corner order).  The whole gather is 98 KB per tile from L2, which also feeds the 1 MB weight stream:
           // done in one burst it ran at the L2 bandwidth roof for 7-8k cycles and delayed the layer it shared the window with;
           // 12 KB per window hides.  Not in layer 0's window: with the cross-tile prefetch that layer's MMAs are done before the
           // tile starts, and the gather's L2 latency (~2 k cycles) sat on the critical path.
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
           }
           if (valid) {
             if (args.smpl_bw) {
-              if (l == 8) {
+              if (l == 7) {
                 const float4 *r4 = reinterpret_cast<const float4 *>(args.smpl_bw + gi * ANINERF_N_BONES) + half * 3;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -646,24 +646,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
                   smpl[4 * q + 3] = w4.w;
                 }
               }
-            } else {
-              float wc;
-              int oc;
-              fast_corner(s_grid, args.grid_dim, px, py, pz, l - 1, wc, oc);
-              const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)oc * ANINERF_N_BONES) + half * 3;
-              float4 c4[3];
+            } else if (l < 8) {
+              // window of layer 1: corners 0 and 1; layers 2..7: corner l (the last layer's window is short and holds the logs)
+              for (int corner = l == 1 ? 0 : l; corner <= l; ++corner) {
+                float wc;
+                int oc;
+                fast_corner(s_grid, args.grid_dim, px, py, pz, corner, wc, oc);
+                const float4 *r4 = reinterpret_cast<const float4 *>(args.vol_w24 + (int64_t)oc * ANINERF_N_BONES) + half * 3;
+                float4 c4[3];
 #pragma unroll
-              for (int q = 0; q < 3; ++q) c4[q] = __ldg(r4 + q);
+                for (int q = 0; q < 3; ++q) c4[q] = __ldg(r4 + q);
 #pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                smpl[4 * q] = fmaf(c4[q].x, wc, smpl[4 * q]);
-                smpl[4 * q + 1] = fmaf(c4[q].y, wc, smpl[4 * q + 1]);
-                smpl[4 * q + 2] = fmaf(c4[q].z, wc, smpl[4 * q + 2]);
-                smpl[4 * q + 3] = fmaf(c4[q].w, wc, smpl[4 * q + 3]);
+                for (int q = 0; q < 3; ++q) {
+                  smpl[4 * q] = fmaf(c4[q].x, wc, smpl[4 * q]);
+                  smpl[4 * q + 1] = fmaf(c4[q].y, wc, smpl[4 * q + 1]);
+                  smpl[4 * q + 2] = fmaf(c4[q].z, wc, smpl[4 * q + 2]);
+                  smpl[4 * q + 3] = fmaf(c4[q].w, wc, smpl[4 * q + 3]);
+                }
               }
             }
           }
-          if (l == 8) ANI_TRACE(5);
+          if (l == 8) {
+            // the head's log(smpl_bw + 1e-9), still inside the last layer's window (12 logf per thread: ~1 k cycles off the tile's tail)
+#pragma unroll
+            for (int k = 0; k < ANINERF_N_BONES / 2; ++k) smpl[k] = logf(smpl[k] + 1e-9f);
+            ANI_TRACE(5);
+          }
         }
         if (NERF && l == VIEW_LAYER_WRITE && !args.density_only) {
           // PE(viewdir) -> its own operand block, while this layer's MMAs run.  Its last reader was the PREVIOUS tile's view layer,
@@ -822,7 +830,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_kernel(const __grid_constant
 #pragma unroll
           for (int k = 0; k < HB; ++k) {
             const float d = __uint_as_float(half ? v[HB + k] : v[k]);
-            bw[k] = logf(smpl[k] + 1e-9f) + (d + bias[k0 + k]);
+            bw[k] = smpl[k] + (d + bias[k0 + k]);             // smpl[]: already log(smpl_bw + 1e-9)
             mx = fmaxf(mx, bw[k]);
           }
           scr[half * TILE_M + row] = mx;
