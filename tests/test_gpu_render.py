@@ -310,3 +310,33 @@ def test_render_other_poses_views_and_backgrounds(dev, pose_seed, voxel, azimuth
             assert np.array_equal(dv['active_index'][:na].cpu().numpy(), np.nonzero(ref['_debug']['pind'].numpy())[0].astype(np.int32))
             assert float((dv['pbw_all'][:na].cpu() - ref['_debug']['pbw_all']).abs().max()) <= BW_TOL
             assert float((dv['raw'].view(ref['raw'].shape).cpu() - ref['raw']).abs().max()) <= RGB_TOL
+
+
+def test_render_frames_equals_per_frame_render(dev):
+    """Renderer.render_frames (the evaluation loop of run.py:59-70 with the next frame's upload in flight) returns, frame by frame,
+    exactly what render(to_device(batch)) returns -- different poses / latent indices per frame, pinned and pageable host batches."""
+    from animatable_nerf_b200 import config, synthetic
+    from animatable_nerf_b200.tpose_nerf_network import Network
+    from animatable_nerf_b200.tpose_renderer import Renderer
+    sd = synthetic.make_state_dict(seed=0)
+    cfg = config.make_cfg(perturb=0., b200_render_only=True)
+    net = Network(cfg)
+    net.load_state_dict(sd)
+    r = Renderer(net.to(dev).eval(), cfg)
+    batches = []
+    for i, (pose, lat) in enumerate(((3, 0), (7, 5), (11, 9), (3, 0))):
+        frame = synthetic.make_frame(pose_seed=pose, body_seed=1, voxel=0.05, latent_index=lat)
+        K, R, T = synthetic.make_camera(frame, 96, 96, focal=100.0)
+        ro, rd, near, far, _ = O.get_rays_within_bounds(96, 96, K, R, T, frame['wbounds'])
+        b = synthetic.make_render_batch(frame, ro, rd, near, far)
+        if i % 2 == 0:
+            b = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        batches.append(b)
+    want = [r.render(r.to_device(b, dev)) for b in batches]
+    got = list(r.render_frames(iter(batches), dev))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert set(g) == set(w)
+        for k in w:
+            assert not g[k].is_cuda and torch.equal(g[k], w[k]), k
+    assert list(r.render_frames(iter([]), dev)) == []
