@@ -9,18 +9,21 @@
 // accumulator buffer is exactly big enough for the next layer's A operand (x1: 128 of its 256 columns, x3: all of them) -- and
 // layer l+1 is issued in the .ts form (A from tensor memory, `tcgen05.mma [d], [a], b_desc`), accumulating into the OTHER
 // buffer.  Only the 64-wide input encodings (PE(xyz), PE(viewdir)) are shared-memory operands (K-major SWIZZLE_128B blocks).
-// Weights stream from L2 through a ring of 32 KB stages filled by bulk TMA copies (cp.async.bulk) of pre-packed
-// SWIZZLE_128B blocks; each CTA of the pair loads HALF of every block (the M=256 MMA reads B from both CTAs), which halves the
-// L2 -> SM weight traffic per sample.  One thread of the leader CTA issues tcgen05.mma (M=256, N<=256, K=16); eight
-// epilogue warps per CTA (two threads per row, each owning half of every 64-column quarter).  Positional encoding is generated
-// in-kernel straight into the A operand; the last epilogue is the field's head (softmax + inverse LBS, or alpha/rgb activation
-// + tbounds masking + scatter).
+// Weights stream from L2 through a ring of stages (split precision: 4 x 32 KB, single pass: 2 x 64 KB + a 16 KB auxiliary slot)
+// filled by bulk TMA copies (cp.async.bulk) of pre-packed SWIZZLE_128B blocks; each CTA of the pair loads HALF of every block (the
+// M=256 MMA reads B from both CTAs), which halves the L2 -> SM weight traffic per sample.  One ELECTED thread of the leader CTA
+// issues tcgen05.mma (M=256, N<=256, K=16); eight epilogue warps per CTA (two threads per row, each owning half of every
+// 64-column quarter).  Positional encoding is generated in-kernel straight into the A operand; the last epilogue is the field's
+// head (softmax + inverse LBS, or alpha/rgb activation + tbounds masking + scatter).
 //
-// Why: tools/bench_mma.cu (profiles/r02_mma_microbench.md).  (1) An M=256 N=256 K=16 MMA takes 152 cycles with both operands in the
-// SWIZZLE_NONE core-matrix layout of round 1, 129.7 with SWIZZLE_128B, 128.3 with A in tensor memory (floor 128).  (2) No MMA
-// retires faster than ~105 cycles whatever its N, so the N = 128 halves of round 1 cost 2 x 105..131 cycles per K=16 slice.
-// (3) The ONE thread that issues the MMAs is the scarcest resource of the kernel: every dependent scalar instruction, mbarrier
-// try_wait (~100 cycles even when complete) and commit between two MMAs is tensor-pipe idle time once it exceeds the MMA time.
+// Why: tools/bench_mma.cu (profiles/r02_mma_microbench_*.log), DESIGN.md section 5.  (1) Issued from an elected lane with
+// loop-invariant descriptors an M=256 K=16 MMA retires in 129.4 (N=256) / 68.5 (N=128) / 28 (N=32, A in tensor memory) cycles in
+// every operand layout; issued from `lane == 0` of a divergent warp the compiler's ELECT / BRA.U.ANY waterfall loop makes the
+// ISSUE cost ~105 cycles per MMA (what looked like a hardware floor in the first version of the benchmark and of this kernel).
+// (2) The ONE thread that issues the MMAs is the scarcest resource of the kernel: every dependent scalar instruction, mbarrier
+// try_wait (~100 cycles even when complete) and commit between two MMAs is tensor-pipe idle time once the ~7-deep MMA queue
+// has drained.  (3) With A in shared memory the operand reads, the epilogue's writes and the weight ring share one 128 B/cycle
+// port; with A in tensor memory the port carries the weights only.
 //
 // Pipelining (QP, "quarter pipelining"): the epilogue publishes the next layer's operand one 64-column K-block at a time
 // (a_ready[q]), so the MMAs of layer l+1 start as soon as the first quarter is written and run while the epilogue produces the
