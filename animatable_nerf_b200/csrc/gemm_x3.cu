@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_cons
     if (chunk + 1 < n_chunks) load_chunk(chunk + 1);          // in flight while this chunk is published and multiplied
     fence_proxy_async();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // (an ELECTED lane: inside `if (threadIdx.x == 0)` ptxas wraps every MMA in a waterfall loop -- ~105 cycles of issue per MMA,
+    // on the critical path of the chunk loop)
+    if (threadIdx.x < 32 && elect_one()) {
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < G_KC / 16; ++k) {
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_x3_kernel(const __grid_cons
       umma_commit<1>(bar0 + 8 * s);
     }
   }
-  if (threadIdx.x == 0) umma_commit<1>(bar0 + 8 * NS);   // arrives once every MMA above has retired
+  if (threadIdx.x < 32 && elect_one()) umma_commit<1>(bar0 + 8 * NS);   // arrives once every MMA above has retired (same lane as the issuer)
   const bool any = chunk > 0;
   if (any) mbar_wait(bar0 + 8 * NS, 0, 21);
   tc_fence_after();
