@@ -700,11 +700,10 @@ __global__ void __launch_bounds__(256) mask_kernel(SampleSetup p, const float *_
         world_to_pose(s_frame, wx, wy, wz, px, py, pz);
         float w[8];
         int off[8];
-        trilinear_corners(s_grid, px, py, pz, w, off);
+        trilinear_corners_clamped(s_grid, px, py, pz, w, off);
         float pn = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (off[k] >= 0) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
+        for (int k = 0; k < 8; ++k) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
         act = pn < p.norm_th;
         unsigned long long key = ((unsigned long long)float_key(pn) << 32) | (unsigned long long)(chunk_base + it * 256 + threadIdx.x);
         best = key < best ? key : best;
@@ -900,11 +899,10 @@ __global__ void __launch_bounds__(256) mask_points_kernel(const float *__restric
     ppts[3 * i + 2] = pz;
     float w[8];
     int off[8];
-    trilinear_corners(grid, px, py, pz, w, off);
+    trilinear_corners_clamped(grid, px, py, pz, w, off);
     float pn = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (off[k] >= 0) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
+    for (int k = 0; k < 8; ++k) pn = __fadd_rn(pn, __fmul_rn(__ldg(dist + off[k]), w[k]));
     mask[i] = pn < norm_th ? 1 : 0;
     best = ((unsigned long long)float_key(pn) << 32) | (unsigned long long)(uint32_t)(i % chunk_pts);
   }
