@@ -192,26 +192,40 @@ class Renderer:
 
     def render_frames(self, host_batches, device=None):
         """The evaluation loop of run.py:59-70 (`for batch in data_loader: batch[k] = batch[k].cuda(); renderer.render(batch)`) as
-        a generator over HOST batches: yields `render(to_device(batch))` frame by frame, with the NEXT batch's upload already in
-        flight on a second stream while the current frame renders (the 18 MB blend-weight volume of a frame takes ~0.35 ms of PCIe
-        time -- a seventh of the frame's kernels).  Results are identical to calling `render(to_device(batch))` per batch."""
+        a generator over HOST batches: yields `render(to_device(batch))` frame by frame, in order, with
+          * the NEXT batch's upload in flight on a second stream while the current frame renders (the 18 MB blend-weight volume of
+            a frame takes ~0.35 ms of PCIe time -- a seventh of the frame's kernels), and
+          * in the render-only evaluation mode, the PREVIOUS frame's maps downloaded on a third stream while the current frame
+            renders: frame i is handed out once frame i+1 has been enqueued, so the device never waits for the host loop.
+        Results are identical to calling `render(to_device(batch))` per batch."""
         dev = torch.device(device) if device is not None else next(self.net.parameters()).device
         main = torch.cuda.current_stream(dev)
-        side = self.__dict__.get('_copy_stream')
+        side, down = self.__dict__.get('_copy_stream'), self.__dict__.get('_down_stream')
         if side is None:
             side = self.__dict__['_copy_stream'] = torch.cuda.Stream(dev)
+            down = self.__dict__['_down_stream'] = torch.cuda.Stream(dev)
+        cfg = self.cfg
+        lagged = bool(config.get(cfg, 'b200_render_only')) and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters()))
 
         def upload(b):
-            side.wait_stream(main)                       # (buffers the allocator hands out may have just been used on `main`)
+            begun = torch.cuda.Event()
+            begun.record(main)
+            side.wait_event(begun)                       # (not before the work already queued on `main`: buffers are recycled across streams)
             with torch.cuda.stream(side):
                 d = self.to_device(b, dev)
                 ev = torch.cuda.Event()
                 ev.record(side)
             return d, ev
 
+        def finish(p):
+            host, ev, _keep = p
+            ev.synchronize()
+            return host
+
         it = iter(host_batches)
         first = next(it, None)
         cur = upload(first) if first is not None else None
+        pending = None
         while cur is not None:
             nb = next(it, None)
             ahead = upload(nb) if nb is not None else None      # enqueued BEFORE this frame's kernels: the copy engine overlaps them
@@ -220,8 +234,34 @@ class Renderer:
             for v in d.values():
                 if torch.is_tensor(v) and v.is_cuda:
                     v.record_stream(main)
-            yield self.render(d)
+            if lagged:
+                with torch.no_grad():
+                    R = d['ray_o'].shape[1]
+                    t_rand = None
+                    if config.get(cfg, 'perturb') > 0. and self.net.training:
+                        t_rand = torch.rand(1, R, int(config.get(cfg, 'N_samples'))).to(dev)      # CPU generator, as tpose_renderer.py:35
+                    out = self.render_device(d, t_rand=t_rand, want_bw=False)
+                    ret = {'rgb_map': out['rgb_map'].view(1, R, 3), 'acc_map': out['acc_map'].view(1, R), 'depth_map': out['depth_map'].view(1, R)}
+                    rendered = torch.cuda.Event()
+                    rendered.record(main)
+                    host = {}
+                    with torch.cuda.stream(down):
+                        down.wait_event(rendered)
+                        for k, v in ret.items():
+                            h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                            h.copy_(v, non_blocking=True)
+                            v.record_stream(down)
+                            host[k] = h
+                        done = torch.cuda.Event()
+                        done.record(down)
+                if pending is not None:
+                    yield finish(pending)
+                pending = (host, done, (d, out))
+            else:
+                yield self.render(d)
             cur = ahead
+        if pending is not None:
+            yield finish(pending)
 
     def _render_eval(self, batch):
         cfg = self.cfg

@@ -482,24 +482,76 @@ def run_b200(args):
         h2d += (b_ - a_) * 4 - host['pbw'].numel() * 4
     pinned_out = torch.empty(n_rays, 5, dtype=torch.float32).pin_memory()
 
+    # N > 1, pipelined like Renderer.render_frames: the NEXT frame's upload (its rays + 1/N of the volume + the NVLink pushes + the
+    # volume barrier) runs on a second stream while this frame renders; rank 0 copies the gathered image to a staging buffer and
+    # downloads it on a third stream while the next frame renders (PeerVolume and the staging buffer double-buffer the data).
+    # Every step still uploads one frame's inputs and downloads one frame's image inside the timed region.
+    e2e_state = {'cur': None, 'd2h': None, 'rendered': None}
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    down = torch.cuda.Stream(dev) if world > 1 else None
+    stage_img = torch.empty(n_rays, 5, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+
+    def upload_async():
+        # starts when (a) this step has begun on the main stream (not under the L2 flush that precedes it) and (b) the frame before
+        # the one now rendering is done on every rank (its gather barrier has passed): PeerVolume's buffer of that frame is reused
+        main = torch.cuda.current_stream(dev)
+        begun = torch.cuda.Event()
+        begun.record(main)
+        side.wait_event(begun)
+        with torch.cuda.stream(side):
+            if pvol is not None:
+                b = renderer.to_device({k: v for k, v in host.items() if k != 'pbw'}, dev)
+                b['pbw'] = pvol.upload(host['pbw'])
+            else:
+                b = renderer.to_device(host, dev)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return b, ev
+
     def step_e2e():
         if world == 1:
             return renderer.render(renderer.to_device(host, dev))
         main = torch.cuda.current_stream(dev)
-        if pvol is not None:
-            b = renderer.to_device({k: v for k, v in host.items() if k != 'pbw'}, dev)
-            b['pbw'] = pvol.upload(host['pbw'])
-        else:
-            b = renderer.to_device(host, dev)
+        if e2e_state['cur'] is None:
+            e2e_state['cur'] = upload_async()
+        ahead = upload_async()
+        b, ev = e2e_state['cur']
+        main.wait_event(ev)
+        for v in b.values():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(main)
         out, img = render_and_gather(b)
-        res = img if rank == 0 else None
-        if res is not None:
-            dst = pinned_out[:res.shape[0]]
-            dst.copy_(res, non_blocking=True)
-        main.synchronize()
-        return res
+        if rank == 0:
+            prev = e2e_state['d2h']
+            if prev is not None:
+                prev.synchronize()                       # the host has the previous frame's image (long complete: no stall) ...
+                main.wait_event(prev)                    # ... and the staging buffer is free
+            stage_img[:img.shape[0]].copy_(img)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(done)
+                pinned_out[:img.shape[0]].copy_(stage_img[:img.shape[0]], non_blocking=True)
+                e2e_state['d2h'] = torch.cuda.Event()
+                e2e_state['d2h'].record(down)
+        # the host does NOT wait for this frame: it runs one frame ahead, bounded by the wait on the previous frame's work below
+        rendered = torch.cuda.Event()
+        rendered.record(main)
+        if e2e_state['rendered'] is not None:
+            e2e_state['rendered'].synchronize()
+        e2e_state['rendered'] = rendered
+        e2e_state['cur'] = ahead
+        return img if rank == 0 else None
 
-    def timed(fn, steps, profile=False):
+    def finish_e2e():                                    # the last frame's render and download belong to the timed region
+        if world == 1:
+            torch.cuda.synchronize(dev)                  # (render_frames: one frame is in flight when next() returns)
+        if world > 1:
+            if e2e_state['d2h'] is not None:
+                torch.cuda.current_stream(dev).wait_event(e2e_state['d2h'])
+            torch.cuda.current_stream(dev).synchronize()
+
+    def timed(fn, steps, profile=False, finish=None):
         evs = []
         L.aninerf_profile_enable(1 if profile else 0)
         barrier()
@@ -512,6 +564,12 @@ def run_b200(args):
             b.record()
             evs.append((a, b))
             del r
+        if finish is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            finish()
+            b.record()
+            evs.append((a, b))
         barrier()
         clocks.windows.append((t_begin, time.time()))
         L.aninerf_profile_enable(0)
@@ -551,7 +609,7 @@ def run_b200(args):
     launches = L.aninerf_launch_count() - launches0
     L.aninerf_profile_read(ms_buf, calls_buf, 1)
     stage_ms = {name: (ms_buf[i] / max(1, calls_buf[i])) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
-    e2e_ms = timed(lambda: step_e2e(), args.steps)
+    e2e_ms = timed(lambda: step_e2e(), args.steps, finish=finish_e2e)
     e2e_sync_ms = None
     if world == 1:
         # The evaluation loop as a user writes it against this package: `for out in renderer.render_frames(host_batches)` --
@@ -562,10 +620,10 @@ def run_b200(args):
         frames = renderer.render_frames(itertools.repeat(host), dev)
         for _ in range(3):
             next(frames)
-        e2e_ms = timed(lambda: next(frames), args.steps)
+        e2e_ms = timed(lambda: next(frames), args.steps, finish=finish_e2e)
         frames.close()
     # a longer run of the same step (the K timed steps last tens of milliseconds, at N = 8 ~10 ms: one disturbance moves them by %)
-    long_frames = 200
+    long_frames = 500          # (at N = 8 the 500 frames last > 0.2 s)
     long_ms = timed(lambda: step_device(), long_frames)
     # ---- the FULL contract (the package's default mode and what the reference / the CPU arm evaluate): posed + canonical
     # blend-weight field + NeRF, dense raw, pbw / tbw rows -- device-timed, and end to end through Renderer.render(batch) --------
@@ -649,9 +707,10 @@ def run_b200(args):
                    'weights': 'random init, seed 0, reference checkpoint layout'},
         'e2e': {'value': samples / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'synchronous_ms_per_step': (e2e_sync_ms / args.steps) if e2e_sync_ms is not None else None,
-                'call': ('next(Renderer.render_frames(pinned host batches)) -> host maps: one upload (next frame, second stream) + one render + one download '
-                         'per step; synchronous_ms_per_step = Renderer.render(Renderer.to_device(batch)) per step' if world == 1 else
-                         'per rank: to_device(its rays) + PeerVolume.upload(1/N of pbw, NVLink push) + render_device(peers=...) + barrier; rank 0 downloads the image'),
+                'call': ('next(Renderer.render_frames(pinned host batches)) -> host maps: per step one upload (next frame, second stream), one render, one download '
+                         '(previous frame, third stream); synchronous_ms_per_step = Renderer.render(Renderer.to_device(batch)) per step' if world == 1 else
+                         'per rank and step: to_device(its rays) + PeerVolume.upload(1/N of pbw, NVLink push) of the NEXT frame on a second stream, '
+                         'render_device(peers=...) + barrier of this one, rank 0 downloads the image on a third stream (overlapping the next frame)'),
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(n_rays * 20)},
         'gpu_launches': int(launches),
         'long_run': {'frames': long_frames, 'ms_per_frame': long_ms / long_frames, 'samples_per_s': samples / (long_ms / long_frames * 1e-3)},
