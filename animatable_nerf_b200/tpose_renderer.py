@@ -42,12 +42,14 @@ class Renderer:
     FRAME_KEYS_RENDER = ('A', 'R', 'Th', 'pbw', 'pbounds', 'tbounds', 'wbounds', 'latent_index', 'bw_latent_index', 'ray_o', 'ray_d', 'near', 'far',
                          'msks', 'Ks', 'RT', 'H', 'W')
 
-    def to_device(self, batch, device=None, non_blocking=True):
+    def to_device(self, batch, device=None, non_blocking=True, pool=None):
         """Host batch -> device batch (the `batch[k] = batch[k].cuda()` loop of run.py:63-66), moving only the keys the
         configured mode READS: in render-only mode (`b200_render_only`) the canonical volume `tbw` (11 MB per frame), `occupancy`,
         `rgb`, ... never reach a kernel and stay on the host.  The dozen small tensors of a batch (bone matrices, bounds, pose,
         indices: a few KB together) travel as ONE staged copy instead of a dozen 10-microsecond `.to()` calls; pinned host tensors
-        are copied asynchronously on the current stream."""
+        are copied asynchronously on the current stream.
+        pool: a dict owned by the caller; the device tensors (and the staging buffers of the small ones) are kept in it and REUSED by
+        the next call with the same pool and shapes -- no allocation in a steady-state frame loop (`render_frames` rotates three)."""
         dev = torch.device(device) if device is not None else next(self.net.parameters()).device
         render_only = bool(config.get(self.cfg, 'b200_render_only'))
         out, small = {}, []
@@ -57,6 +59,12 @@ class Renderer:
             elif not render_only or k in self.FRAME_KEYS_RENDER:
                 if v.device.type == 'cpu' and v.numel() * v.element_size() <= 16384 and v.numel() > 0:
                     small.append((k, v))
+                elif pool is not None and v.device.type == 'cpu':
+                    buf = pool.get(k)
+                    if buf is None or buf.shape != v.shape or buf.dtype != v.dtype or buf.device != dev:
+                        buf = pool[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                    buf.copy_(v, non_blocking=non_blocking)
+                    out[k] = buf
                 else:
                     out[k] = v.to(dev, non_blocking=non_blocking)
         if small:
@@ -64,16 +72,24 @@ class Renderer:
             for _, v in small:
                 offs.append(total)
                 total += (v.numel() * v.element_size() + 15) // 16 * 16
-            stage, done = self.__dict__.get('_stage'), self.__dict__.get('_stage_done')
+            store = pool if pool is not None else self.__dict__
+            stage, done = store.get('_stage'), store.get('_stage_done')
             if done is not None:
                 done.synchronize()                      # the previous staged copy has left the pinned buffer
             if stage is None or stage.numel() < total:
-                stage = self.__dict__['_stage'] = torch.empty(max(total, 65536), dtype=torch.uint8).pin_memory()
+                stage = store['_stage'] = torch.empty(max(total, 65536), dtype=torch.uint8).pin_memory()
             for (k, v), o in zip(small, offs):
                 stage[o:o + v.numel() * v.element_size()].copy_(v.contiguous().view(-1).view(torch.uint8))
-            d = stage[:total].to(dev, non_blocking=non_blocking)
+            if pool is not None:
+                d = pool.get('_stage_dev')
+                if d is None or d.numel() < total or d.device != dev:
+                    d = pool['_stage_dev'] = torch.empty(stage.numel(), dtype=torch.uint8, device=dev)
+                d = d[:total]
+                d.copy_(stage[:total], non_blocking=non_blocking)
+            else:
+                d = stage[:total].to(dev, non_blocking=non_blocking)
             if dev.type == 'cuda':
-                done = self.__dict__['_stage_done'] = torch.cuda.Event()
+                done = store['_stage_done'] = torch.cuda.Event()
                 done.record(torch.cuda.current_stream(dev))
             for (k, v), o in zip(small, offs):
                 out[k] = d[o:o + v.numel() * v.element_size()].view(v.dtype).view(v.shape)
@@ -207,20 +223,28 @@ class Renderer:
         cfg = self.cfg
         lagged = bool(config.get(cfg, 'b200_render_only')) and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters()))
 
+        pools = self.__dict__.setdefault('_frame_pools', [{}, {}, {}])      # inputs of the frame ahead, the one rendering, the one downloading
+        turn = [0]
+
         def upload(b):
             begun = torch.cuda.Event()
             begun.record(main)
-            side.wait_event(begun)                       # (not before the work already queued on `main`: buffers are recycled across streams)
+            side.wait_event(begun)                       # (the pool's previous user -- three frames back -- is complete by then)
             with torch.cuda.stream(side):
-                d = self.to_device(b, dev)
+                d = self.to_device(b, dev, pool=pools[turn[0] % 3])
+                turn[0] += 1
                 ev = torch.cuda.Event()
                 ev.record(side)
             return d, ev
 
         def finish(p):
-            host, ev, _keep = p
+            staged, ev, _keep = p
             ev.synchronize()
-            return host
+            # ordinary CPU tensors, as `.cpu()` returns them; the pinned staging buffers rotate (allocating pinned memory per frame
+            # costs a cudaHostAlloc -- 10-50 ms -- whenever the caching host allocator has no block whose stream events are done)
+            return {k: v.clone() for k, v in staged.items()}
+
+        rings = self.__dict__.setdefault('_host_rings', [{}, {}, {}])
 
         it = iter(host_batches)
         first = next(it, None)
@@ -244,11 +268,13 @@ class Renderer:
                     ret = {'rgb_map': out['rgb_map'].view(1, R, 3), 'acc_map': out['acc_map'].view(1, R), 'depth_map': out['depth_map'].view(1, R)}
                     rendered = torch.cuda.Event()
                     rendered.record(main)
-                    host = {}
+                    host, ring = {}, rings[turn[0] % 3]
                     with torch.cuda.stream(down):
                         down.wait_event(rendered)
                         for k, v in ret.items():
-                            h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                            h = ring.get(k)
+                            if h is None or h.shape != v.shape or h.dtype != v.dtype:
+                                h = ring[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                             h.copy_(v, non_blocking=True)
                             v.record_stream(down)
                             host[k] = h

@@ -551,9 +551,16 @@ def run_b200(args):
                 torch.cuda.current_stream(dev).wait_event(e2e_state['d2h'])
             torch.cuda.current_stream(dev).synchronize()
 
-    def timed(fn, steps, profile=False, finish=None):
+    step_stats = {}
+
+    def timed(fn, steps, profile=False, finish=None, tag=None):
+        # (the cyclic garbage collector is paused inside the timed region: a generation-2 pass over the interpreter's heap takes
+        # tens of milliseconds -- more than the whole region at N = 8 -- and is not part of a frame)
+        import gc
         evs = []
         L.aninerf_profile_enable(1 if profile else 0)
+        gc.collect()
+        gc.disable()
         barrier()
         t_begin = time.time()
         for _ in range(steps):
@@ -573,7 +580,11 @@ def run_b200(args):
         barrier()
         clocks.windows.append((t_begin, time.time()))
         L.aninerf_profile_enable(0)
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        gc.enable()
+        per = [a.elapsed_time(b) for a, b in evs]
+        if tag:
+            step_stats[tag] = {'min_ms': min(per[:steps]), 'median_ms': float(np.median(per[:steps])), 'max_ms': max(per[:steps])}
+        ms = sum(per)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -605,11 +616,11 @@ def run_b200(args):
     ms_buf, calls_buf = (C.c_double * 9)(), (C.c_int64 * 9)()
     L.aninerf_profile_read(ms_buf, calls_buf, 1)
     launches0 = L.aninerf_launch_count()
-    total_ms = timed(lambda: step_device(), args.steps, profile=True)
+    total_ms = timed(lambda: step_device(), args.steps, profile=True, tag='device')
     launches = L.aninerf_launch_count() - launches0
     L.aninerf_profile_read(ms_buf, calls_buf, 1)
     stage_ms = {name: (ms_buf[i] / max(1, calls_buf[i])) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
-    e2e_ms = timed(lambda: step_e2e(), args.steps, finish=finish_e2e)
+    e2e_ms = timed(lambda: step_e2e(), args.steps, finish=finish_e2e, tag='e2e')
     e2e_sync_ms = None
     if world == 1:
         # The evaluation loop as a user writes it against this package: `for out in renderer.render_frames(host_batches)` --
@@ -618,9 +629,9 @@ def run_b200(args):
         import itertools
         e2e_sync_ms = e2e_ms
         frames = renderer.render_frames(itertools.repeat(host), dev)
-        for _ in range(3):
+        for _ in range(max(args.warmup, 8)):             # (the three rotating input / staging buffer sets are allocated here)
             next(frames)
-        e2e_ms = timed(lambda: next(frames), args.steps, finish=finish_e2e)
+        e2e_ms = timed(lambda: next(frames), args.steps, finish=finish_e2e, tag='e2e')
         frames.close()
     # a longer run of the same step (the K timed steps last tens of milliseconds, at N = 8 ~10 ms: one disturbance moves them by %)
     long_frames = 500          # (at N = 8 the 500 frames last > 0.2 s)
@@ -713,6 +724,7 @@ def run_b200(args):
                          'render_device(peers=...) + barrier of this one, rank 0 downloads the image on a third stream (overlapping the next frame)'),
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(n_rays * 20)},
         'gpu_launches': int(launches),
+        'step_ms': step_stats,          # per-step spread of the timed regions (rank 0's events): a single disturbed step shows here
         'long_run': {'frames': long_frames, 'ms_per_frame': long_ms / long_frames, 'samples_per_s': samples / (long_ms / long_frames * 1e-3)},
         'full_contract': full_contract,
         'clocks': clk,
