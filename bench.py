@@ -486,7 +486,8 @@ def run_b200(args):
     # volume barrier) runs on a second stream while this frame renders; rank 0 copies the gathered image to a staging buffer and
     # downloads it on a third stream while the next frame renders (PeerVolume and the staging buffer double-buffer the data).
     # Every step still uploads one frame's inputs and downloads one frame's image inside the timed region.
-    e2e_state = {'cur': None, 'd2h': None, 'rendered': None}
+    e2e_state = {'cur': None, 'd2h': None, 'rendered': None, 'n': 0}
+    e2e_pools = [{}, {}, {}]
     side = torch.cuda.Stream(dev) if world > 1 else None
     down = torch.cuda.Stream(dev) if world > 1 else None
     stage_img = torch.empty(n_rays, 5, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
@@ -499,11 +500,13 @@ def run_b200(args):
         begun.record(main)
         side.wait_event(begun)
         with torch.cuda.stream(side):
+            pool = e2e_pools[e2e_state['n'] % 3]         # rotating device buffers: no allocation per frame
+            e2e_state['n'] += 1
             if pvol is not None:
-                b = renderer.to_device({k: v for k, v in host.items() if k != 'pbw'}, dev)
+                b = renderer.to_device({k: v for k, v in host.items() if k != 'pbw'}, dev, pool=pool)
                 b['pbw'] = pvol.upload(host['pbw'])
             else:
-                b = renderer.to_device(host, dev)
+                b = renderer.to_device(host, dev, pool=pool)
             ev = torch.cuda.Event()
             ev.record(side)
         return b, ev
