@@ -71,15 +71,31 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed regions run.  In-process NVML (nvidia_ml_py: one nvmlInit before the
+    warm-up, then two light queries every 20 ms from a thread) when it is available: the `nvidia-smi -lms` process it replaces
+    stalled kernel launches for 10-50 ms on roughly one query in ten (its per-sample power / reasons queries take the driver
+    lock), which showed up as single disturbed steps in 1 of 7 end-to-end regions.  Falls back to nvidia-smi."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
         self.windows = []          # (t0, t1) of the timed regions: only samples taken under load are reported
+        self.nvml, self.handle, self.max_mhz, self._stop = None, None, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', os.environ.get('ANINERF_SMI_MS', '200'),
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -87,15 +103,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        period = float(os.environ.get('ANINERF_NVML_MS', '20')) * 1e-3
+        while not self._stop:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                act = lambda bit: 'Active' if (r & bit) else 'Not Active'
+                self.rows.append((time.time(), [str(mhz), str(self.max_mhz), '', act(n.nvmlClocksThrottleReasonHwSlowdown),
+                                                act(n.nvmlClocksThrottleReasonHwThermalSlowdown), act(n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                                act(n.nvmlClocksThrottleReasonSwPowerCap)]))
+            except Exception:
+                pass
+            time.sleep(period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is None and self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
-        self.proc.terminate()
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         inside = [r for t, r in self.rows if any(a <= t <= b for a, b in self.windows)]
@@ -110,7 +144,8 @@ class ClockSampler:
                         reasons.add(n)
             except Exception:
                 continue
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm),
+                'source': 'nvml (in-process)' if self.nvml is not None else 'nvidia-smi -lms'}
 
 
 def build_workload(size):
