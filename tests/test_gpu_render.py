@@ -324,7 +324,7 @@ def test_render_frames_equals_per_frame_render(dev):
     net.load_state_dict(sd)
     r = Renderer(net.to(dev).eval(), cfg)
     batches = []
-    for i, (pose, lat) in enumerate(((3, 0), (7, 5), (11, 9), (3, 0))):
+    for i, (pose, lat) in enumerate(((3, 0), (7, 5), (11, 9), (5, 2), (13, 7))):      # five frames: the three rotating buffer sets are reused
         frame = synthetic.make_frame(pose_seed=pose, body_seed=1, voxel=0.05, latent_index=lat)
         K, R, T = synthetic.make_camera(frame, 96, 96, focal=100.0)
         ro, rd, near, far, _ = O.get_rays_within_bounds(96, 96, K, R, T, frame['wbounds'])
