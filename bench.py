@@ -659,7 +659,7 @@ def run_b200(args):
     L.aninerf_profile_read(ms_buf, calls_buf, 1)
     stage_ms = {name: (ms_buf[i] / max(1, calls_buf[i])) for i, name in enumerate(_lib.STAGES) if calls_buf[i]}
     e2e_ms = timed(lambda: step_e2e(), args.steps, finish=finish_e2e, tag='e2e')
-    e2e_sync_ms = None
+    e2e_sync_ms, e2e_identical = None, None
     if world == 1:
         # The evaluation loop as a user writes it against this package: `for out in renderer.render_frames(host_batches)` --
         # every step uploads one frame's inputs from pinned host memory (overlapping the previous frame's kernels on a second
@@ -670,7 +670,16 @@ def run_b200(args):
         for _ in range(max(args.warmup, 8)):             # (the three rotating input / staging buffer sets are allocated here)
             next(frames)
         e2e_ms = timed(lambda: next(frames), args.steps, finish=finish_e2e, tag='e2e')
+        last = next(frames)                              # the pipelined loop returns what the device path computes
+        dev_maps = torch.cat([out['rgb_map'], out['acc_map'][:, None], out['depth_map'][:, None]], dim=1).cpu()
+        e2e_identical = bool(torch.equal(torch.cat([last['rgb_map'][0], last['acc_map'][0][:, None], last['depth_map'][0][:, None]], dim=1), dev_maps))
         frames.close()
+    elif rank == 0:
+        torch.cuda.synchronize(dev)
+        _, img_chk = step_device()
+        e2e_identical = bool(torch.equal(pinned_out[:img_chk.shape[0]], img_chk.cpu()))     # the last image the e2e loop downloaded
+    else:
+        step_device()                                    # (rank 0's check above is a collective step)
     # a longer run of the same step (the K timed steps last tens of milliseconds, at N = 8 ~10 ms: one disturbance moves them by %)
     long_frames = 500          # (at N = 8 the 500 frames last > 0.2 s)
     long_ms = timed(lambda: step_device(), long_frames)
@@ -756,6 +765,7 @@ def run_b200(args):
                    'weights': 'random init, seed 0, reference checkpoint layout'},
         'e2e': {'value': samples / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
                 'synchronous_ms_per_step': (e2e_sync_ms / args.steps) if e2e_sync_ms is not None else None,
+                'identical_to_device_path': e2e_identical,
                 'call': ('next(Renderer.render_frames(pinned host batches)) -> host maps: per step one upload (next frame, second stream), one render, one download '
                          '(previous frame, third stream); synchronous_ms_per_step = Renderer.render(Renderer.to_device(batch)) per step' if world == 1 else
                          'per rank and step: to_device(its rays) + PeerVolume.upload(1/N of pbw, NVLink push) of the NEXT frame on a second stream, '
